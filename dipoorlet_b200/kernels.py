@@ -1,0 +1,238 @@
+"""Thin host wrappers over the C-ABI: torch tensors are the device-memory containers,
+every function enqueues on torch's current CUDA stream and returns without syncing.
+
+Nothing here computes: no torch math on the data path, no CPU fallback. A missing
+`libdpl_b200.so` raises from `_lib.lib()`.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (BLOB_FIELDS, F_NSEG, F_PTR, F_SEGLEN, F_STAT, check, lib, plan_blobs)
+
+_launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def launches():
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous CUDA tensor of {dtype}, got "
+                         f"{t.dtype} on {t.device} (contiguous={t.is_contiguous()})")
+
+
+class BlobBatch:
+    """The dpl_blob table of one batch: a list of contiguous float32 CUDA tensors whose
+    leading dimension is the image index. Keeps the tensors alive until released."""
+
+    def __init__(self, tensors, stat_index=None):
+        self.tensors = list(tensors)
+        n = len(self.tensors)
+        table = np.zeros((n, BLOB_FIELDS), dtype=np.uint64)
+        max_seg = 0
+        for i, t in enumerate(self.tensors):
+            _need(t, torch.float32, f"blob {i}")
+            n_seg = t.shape[0] if t.dim() > 0 else 1
+            seg_len = t.numel() // n_seg if n_seg else 0
+            table[i, F_PTR] = t.data_ptr()
+            table[i, F_NSEG] = n_seg
+            table[i, F_SEGLEN] = seg_len
+            table[i, F_STAT] = i if stat_index is None else stat_index[i]
+            max_seg = max(max_seg, seg_len)
+        self.n_segments, self.n_seg_tiles, self.n_flat_tiles = plan_blobs(table)
+        self.host_table = table
+        self.max_seg_len = max_seg
+        self.n_blobs = n
+        self.device = self.tensors[0].device if n else torch.device("cuda")
+        # small (8 KB for ResNet-50) synchronous-on-stream upload
+        self.table = torch.from_numpy(table.view(np.int64)).to(self.device, non_blocking=False)
+        self.elements = int(sum(int(t.numel()) for t in self.tensors))
+
+    def seg_slices(self):
+        """(offset, n_seg) of every blob in the per-segment output arrays."""
+        base = self.host_table[:, _lib.F_SEG_OUT_BASE].astype(np.int64)
+        nseg = self.host_table[:, F_NSEG].astype(np.int64)
+        return list(zip(base.tolist(), nseg.tolist()))
+
+
+class Workspace:
+    """Grow-only scratch buffer (uint8) reused across launches."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+
+    def get(self, nbytes):
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=self.device)
+        return self.buf
+
+
+def segstats(batch, seg_min, seg_max, seg_abssum=None, seg_nnz=None, blob_min=None, blob_max=None,
+             workspace=None):
+    """K1. seg_*: per-segment outputs (float32/float32/float64/int64[n_segments]);
+    blob_min/blob_max: running per-blob extrema (float32[n_stats]), updated in place."""
+    _need(seg_min, torch.float32, "seg_min")
+    _need(seg_max, torch.float32, "seg_max")
+    _need(seg_abssum, torch.float64, "seg_abssum")
+    _need(seg_nnz, torch.int64, "seg_nnz")
+    _need(blob_min, torch.float32, "blob_min")
+    _need(blob_max, torch.float32, "blob_max")
+    assert seg_min.numel() >= batch.n_segments and seg_max.numel() >= batch.n_segments
+    need = lib().dpl_segstats_scratch_bytes(batch.n_seg_tiles)
+    ws = (workspace or Workspace(batch.device)).get(need)
+    check(lib().dpl_segstats_f32(batch.table.data_ptr(), batch.n_blobs, batch.n_segments,
+                                 batch.n_seg_tiles, seg_min.data_ptr(), seg_max.data_ptr(),
+                                 _lib._ptr(seg_abssum), _lib._ptr(seg_nnz), _lib._ptr(blob_min),
+                                 _lib._ptr(blob_max), ws.data_ptr(), ws.numel(), _stream()),
+          "dpl_segstats_f32")
+    _count(2)
+
+
+def absmax(blob_min, blob_max, data_max):
+    _need(blob_min, torch.float32, "blob_min")
+    _need(blob_max, torch.float32, "blob_max")
+    _need(data_max, torch.float32, "data_max")
+    check(lib().dpl_absmax_f32(blob_min.data_ptr(), blob_max.data_ptr(), data_max.data_ptr(),
+                               data_max.numel(), _stream()), "dpl_absmax_f32")
+    _count()
+
+
+def hist_abs(batch, data_max, counts, bins, variant=0):
+    """K2. counts: int64[n_stats, bins] accumulated in place (uint64 bit pattern)."""
+    _need(data_max, torch.float32, "data_max")
+    _need(counts, torch.int64, "counts")
+    assert counts.numel() % bins == 0
+    check(lib().dpl_hist_abs_f32(batch.table.data_ptr(), batch.n_blobs, batch.n_flat_tiles,
+                                 data_max.data_ptr(), int(bins), counts.data_ptr(), int(variant),
+                                 _stream()), "dpl_hist_abs_f32")
+    _count()
+
+
+def hist_percentile(counts, bins, threshold, data_max, blob_min, blob_max, clip, sel_bin=None):
+    """K3. clip: float32[n_stats, 2]; sel_bin: int32[n_stats] or None."""
+    _need(counts, torch.int64, "counts")
+    _need(clip, torch.float32, "clip")
+    _need(sel_bin, torch.int32, "sel_bin")
+    n_stats = counts.numel() // bins
+    check(lib().dpl_hist_percentile(counts.data_ptr(), n_stats, int(bins), float(threshold),
+                                    data_max.data_ptr(), blob_min.data_ptr(), blob_max.data_ptr(),
+                                    clip.data_ptr(), _lib._ptr(sel_bin), _stream()),
+          "dpl_hist_percentile")
+    _count()
+
+
+def octav(batch, seg_abssum, seg_nnz, k_const, out_s, out_iters=None, max_iter=20, workspace=None):
+    """K4. out_s: float32[n_segments]."""
+    _need(seg_abssum, torch.float64, "seg_abssum")
+    _need(seg_nnz, torch.int64, "seg_nnz")
+    _need(out_s, torch.float32, "out_s")
+    _need(out_iters, torch.int32, "out_iters")
+    need = lib().dpl_octav_scratch_bytes(batch.max_seg_len)
+    ws = (workspace or Workspace(batch.device)).get(need)
+    check(lib().dpl_octav_f32(batch.table.data_ptr(), batch.n_blobs, batch.n_segments,
+                              batch.max_seg_len, seg_abssum.data_ptr(), seg_nnz.data_ptr(),
+                              float(k_const), int(max_iter), out_s.data_ptr(),
+                              _lib._ptr(out_iters), ws.data_ptr(), ws.numel(), _stream()),
+          "dpl_octav_f32")
+    _count()
+
+
+def fakequant(x, scale, zero_point=None, qlo=-128, qhi=127, axis=None, drop_prob=1.0, seed=0,
+              out=None):
+    """K5. scale: float32[C] (C = 1 per-tensor); axis: channel axis for per-channel."""
+    _need(x, torch.float32, "x")
+    _need(scale, torch.float32, "scale")
+    _need(zero_point, torch.int32, "zero_point")
+    y = torch.empty_like(x) if out is None else out
+    _need(y, torch.float32, "out")
+    c = scale.numel()
+    if c == 1:
+        inner = 1
+    else:
+        assert axis is not None and x.shape[axis] == c
+        inner = 1
+        for d in x.shape[axis + 1:]:
+            inner *= d
+    check(lib().dpl_fakequant_f32(x.data_ptr(), y.data_ptr(), x.numel(), scale.data_ptr(),
+                                  _lib._ptr(zero_point), c, inner, int(qlo), int(qhi),
+                                  float(drop_prob), int(seed) & (2 ** 64 - 1), _stream()),
+          "dpl_fakequant_f32")
+    _count()
+    return y
+
+
+def channel_sumdiff(a, b, channels, acc):
+    """K7a. a, b: [n_img, channels, ...]; acc: float64[channels] accumulated in place."""
+    _need(a, torch.float32, "a")
+    _need(b, torch.float32, "b")
+    _need(acc, torch.float64, "acc")
+    assert a.shape == b.shape and a.shape[1] == channels
+    n_img = a.shape[0]
+    inner = a.numel() // (n_img * channels) if a.numel() else 1
+    check(lib().dpl_channel_sumdiff_f32(a.data_ptr(), b.data_ptr(), n_img, channels, inner,
+                                        acc.data_ptr(), _stream()), "dpl_channel_sumdiff_f32")
+    _count()
+
+
+def cosine3(a, b, out):
+    """K7b. a, b: [n_seg, ...]; out: float64[n_seg, 3] (zeroed by the caller)."""
+    _need(a, torch.float32, "a")
+    _need(b, torch.float32, "b")
+    _need(out, torch.float64, "out")
+    n_seg = a.shape[0]
+    check(lib().dpl_cosine3_f32(a.data_ptr(), b.data_ptr(), n_seg, a.numel() // max(n_seg, 1),
+                                out.data_ptr(), _stream()), "dpl_cosine3_f32")
+    _count()
+
+
+def adaround_init(w, scale):
+    """alpha0 and floor(w/s) for a weight [C_out, ...] with per-channel scale [C_out]
+    (or a single scale)."""
+    _need(w, torch.float32, "w")
+    _need(scale, torch.float32, "scale")
+    c = scale.numel()
+    inner = w.numel() // c
+    alpha = torch.empty_like(w)
+    wfloor = torch.empty_like(w)
+    check(lib().dpl_adaround_init_f32(w.data_ptr(), scale.data_ptr(), c, inner, alpha.data_ptr(),
+                                      wfloor.data_ptr(), _stream()), "dpl_adaround_init_f32")
+    _count()
+    return alpha, wfloor
+
+
+def adaround_weight(wfloor, alpha, scale, qmin, qmax, soft, out=None):
+    c = scale.numel()
+    inner = wfloor.numel() // c
+    wq = torch.empty_like(wfloor) if out is None else out
+    check(lib().dpl_adaround_weight_f32(wfloor.data_ptr(), alpha.data_ptr(), scale.data_ptr(), c,
+                                        inner, float(qmin), float(qmax), 1 if soft else 0,
+                                        wq.data_ptr(), _stream()), "dpl_adaround_weight_f32")
+    _count()
+    return wq
+
+
+def adaround_step(grad_w, wfloor, scale, qmin, qmax, beta, alpha, m, v, step, reg_alpha=0.01,
+                  lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0, reg_out=None):
+    c = scale.numel()
+    inner = wfloor.numel() // c
+    check(lib().dpl_adaround_step_f32(grad_w.data_ptr(), wfloor.data_ptr(), scale.data_ptr(), c,
+                                      inner, float(qmin), float(qmax), float(beta),
+                                      float(reg_alpha), float(lr), float(b1), float(b2), float(eps),
+                                      int(step), float(grad_scale), alpha.data_ptr(), m.data_ptr(),
+                                      v.data_ptr(), _lib._ptr(reg_out), _stream()),
+          "dpl_adaround_step_f32")
+    _count()

@@ -1,0 +1,168 @@
+/*
+ * dpl_b200.h — C-ABI of libdpl_b200.so, the sm_100a calibration / rounding-finetune
+ * kernels behind the Dipoorlet plugin API.
+ *
+ * Conventions
+ *   - every entry point is extern "C", returns 0 on success or a non-zero status
+ *     (a cudaError_t value, or DPL_E_* below); dpl_last_error() gives the text;
+ *   - every `d_*` pointer is a DEVICE pointer owned by the caller (in the Python
+ *     host: torch tensors' data_ptr()); the library never allocates, frees or
+ *     keeps a pointer past the call; work is enqueued on `stream` and the call
+ *     returns without synchronising;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - a "blob" is one activation tensor of the calibrated network for the images
+ *     of the current batch: n_seg images x seg_len float32, contiguous (NCHW per
+ *     image). A "segment" is one image of one blob — the unit the reference takes
+ *     its per-image statistics on.
+ *
+ * Each entry point cites the reference code it replaces (paths relative to the
+ * ModelTC/Dipoorlet checkout).
+ */
+#ifndef DPL_B200_H_
+#define DPL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPL_VERSION 100
+
+#define DPL_E_BADARG 10001   /* null pointer, zero size, unsupported bins ... */
+#define DPL_E_WORKSPACE 10002 /* scratch buffer too small */
+#define DPL_E_UNSUPPORTED 10003
+
+/* Tile sizes (elements) of the launch-wide tilings the planner fills in. */
+#define DPL_SEG_TILE 8192u
+#define DPL_FLAT_TILE 8192u
+
+/* One blob of the current batch. Filled by the caller except the *_begin fields,
+ * which dpl_plan_blobs() computes. The same array is then uploaded to the device
+ * and handed to the kernels. All fields are 8 bytes so that the layout is
+ * identical from C, ctypes and numpy (dtype '<u8', shape [n_blobs, 8]). */
+typedef struct dpl_blob {
+  uint64_t ptr;            /* device address of float32[n_seg * seg_len], 4-byte aligned */
+  uint64_t n_seg;          /* images in the batch */
+  uint64_t seg_len;        /* elements per image */
+  uint64_t seg_out_base;   /* index of this blob's first segment in per-segment outputs */
+  uint64_t seg_tile_begin; /* first tile of this blob in the segment-respecting tiling */
+  uint64_t flat_tile_begin;/* first tile of this blob in the flat (image-agnostic) tiling */
+  uint64_t stat_index;     /* row of this blob in per-blob arrays (data_max, counts, ...) */
+  uint64_t reserved;
+} dpl_blob;
+
+int dpl_version(void);
+const char* dpl_last_error(void);
+
+/* Host-side planner: fills seg_out_base / seg_tile_begin / flat_tile_begin of
+ * host_blobs[0..n) and returns the totals. Pure host arithmetic, no CUDA call. */
+int dpl_plan_blobs(dpl_blob* host_blobs, int n_blobs, uint64_t* n_segments,
+                   uint64_t* n_seg_tiles, uint64_t* n_flat_tiles);
+
+/* Scratch bytes dpl_segstats_f32 needs for a plan with n_seg_tiles tiles. */
+size_t dpl_segstats_scratch_bytes(uint64_t n_seg_tiles);
+
+/* K1 — per-segment min, max, sum|x| and count(|x|>0) of every blob of the batch in
+ * ONE launch (+ a small finalize launch). Replaces the per-image NumPy reductions
+ * `ort_outs[i].max()/.min()` of forward_get_minmax (dipoorlet/forward_net.py:220-235)
+ * and the first line of the OCTAV loop `abs_x.sum() / abs_x[abs_x > 0].size`
+ * (forward_net.py:323-324).
+ *   d_min/d_max: float32[n_segments]; d_abssum: float64[n_segments];
+ *   d_nnz: uint64[n_segments]   (any of d_abssum/d_nnz may be NULL)
+ * Also folds the batch into running per-blob extrema when d_blob_min/d_blob_max
+ * (float32[n_stats], indexed by stat_index, caller-initialised to +inf/-inf) are
+ * non-NULL — the device-resident equivalent of find_clip_val_minmax
+ * (dipoorlet/tensor_cali/basic_algorithm.py:20-21). */
+int dpl_segstats_f32(const dpl_blob* d_blobs, int n_blobs, uint64_t n_segments,
+                     uint64_t n_seg_tiles, float* d_min, float* d_max, double* d_abssum,
+                     uint64_t* d_nnz, float* d_blob_min, float* d_blob_max, void* d_scratch,
+                     size_t scratch_bytes, void* stream);
+
+/* data_max[b] = max(blob_max[b], -blob_min[b]) as float32 — forward_net.py:266-267. */
+int dpl_absmax_f32(const float* d_blob_min, const float* d_blob_max, float* d_data_max,
+                   int n_stats, void* stream);
+
+/* K2 — np.histogram(np.abs(x), bins, (0, data_max)) accumulated over every image of
+ * every blob of the batch in ONE launch, bit-exact with NumPy's uniform-bin path
+ * (float32 edges, edge-corrected index, right edge inclusive, data_max == 0 widened
+ * to (-0.5, 0.5), |x| > data_max dropped). Replaces forward_get_hist's per-image
+ * np.histogram + the np.stack(hist).sum(0) of find_clip_val_hist
+ * (dipoorlet/forward_net.py:265-280, tensor_cali/basic_algorithm.py:37-38).
+ *   d_data_max: float32[n_stats]; d_counts: uint64[n_stats * bins], accumulated into
+ *   (caller zeroes before the first batch). variant: 0 = auto, see dpl_stats.cu. */
+int dpl_hist_abs_f32(const dpl_blob* d_blobs, int n_blobs, uint64_t n_flat_tiles,
+                     const float* d_data_max, int bins, unsigned long long* d_counts,
+                     int variant, void* stream);
+
+/* K3 — percentile clip search over the accumulated histograms, one tensor per CTA,
+ * sequential float64 accumulation so that the selected bin is the reference's.
+ * Replaces find_clip_val_hist's Python loop (tensor_cali/basic_algorithm.py:40-53).
+ *   d_clip: float32[n_stats * 2] = {lo, hi}; d_bin: int32[n_stats] (-1 = fallback to
+ *   full range, basic_algorithm.py:51-53). */
+int dpl_hist_percentile(const unsigned long long* d_counts, int n_stats, int bins,
+                        double threshold, const float* d_data_max, const float* d_blob_min,
+                        const float* d_blob_max, float* d_clip, int* d_bin, void* stream);
+
+/* K4 — OCTAV fixed point per segment (the 'mse' calibrator): one persistent CTA per
+ * segment, HBM read once, survivors {|x| > s} compacted into an L2-resident scratch.
+ * Replaces forward_net_octav's NumPy loop (dipoorlet/forward_net.py:316-330).
+ *   k_const = 1 / 4**8 / 3 / unsigned; d_s: float32[n_segments]; d_iters (optional):
+ *   int32[n_segments] updates taken; needs d_abssum / d_nnz from dpl_segstats_f32 for
+ *   s0 and a scratch of dpl_octav_scratch_bytes(longest seg_len) bytes. */
+size_t dpl_octav_scratch_bytes(uint64_t max_seg_len);
+int dpl_octav_f32(const dpl_blob* d_blobs, int n_blobs, uint64_t n_segments,
+                  uint64_t max_seg_len, const double* d_abssum, const uint64_t* d_nnz,
+                  double k_const, int max_iter, float* d_s, int* d_iters, void* d_scratch,
+                  size_t scratch_bytes, void* stream);
+
+/* K5 — fake quantisation y = (clamp(rne(x / scale) + zp, qlo, qhi) - zp) * scale.
+ * Per-tensor (n_channels = 1) or per-channel along an outer axis: element i belongs
+ * to channel (i / inner) % n_channels. Replaces the QuantizeLinear/DequantizeLinear
+ * pair emitted by make_quant_dequant (dipoorlet/quantize.py:197-239, executed inside
+ * onnxruntime) and quant_acti (weight_transform/ada_quant_layer.py:28-36).
+ * drop_prob < 1 keeps x where a counter-based uniform draw >= drop_prob (QDrop). */
+int dpl_fakequant_f32(const float* d_x, float* d_y, uint64_t n, const float* d_scale,
+                      const int32_t* d_zero_point, int n_channels, uint64_t inner, int qlo,
+                      int qhi, float drop_prob, uint64_t seed, void* stream);
+
+/* K7a — per-channel mean of (a - b) over (N, H, W): out[c] (+)= sum / count.
+ * Replaces update_conv_node_bias (weight_transform/bias_correction.py:10-13).
+ *   a, b: float32[n_img, channels, inner]; d_sum: float64[channels] accumulated. */
+int dpl_channel_sumdiff_f32(const float* d_a, const float* d_b, uint64_t n_img,
+                            uint64_t channels, uint64_t inner, double* d_sum, void* stream);
+
+/* K7b — per-segment sum(a*b), sum(a*a), sum(b*b) for cos_similarity
+ * (dipoorlet/utils.py:273-278). d_out: float64[n_seg * 3]. */
+int dpl_cosine3_f32(const float* d_a, const float* d_b, uint64_t n_seg, uint64_t seg_len,
+                    double* d_out, void* stream);
+
+/* K6 helpers — AdaRound elementwise pieces around the conv/GEMM re-evaluation
+ * (weight_transform/ada_quant_layer.py:39-50,96-110; adaround.py:119-144). */
+
+/* alpha0 = -log((zeta-gamma)/(rest-gamma) - 1), rest = w/s - floor(w/s); also writes
+ * floor(w/s). Per-channel scale along axis 0 (inner = elements per out channel). */
+int dpl_adaround_init_f32(const float* d_w, const float* d_scale, int n_channels,
+                          uint64_t inner, float* d_alpha, float* d_wfloor, void* stream);
+
+/* w_soft = clamp(wfloor + h(alpha), qmin, qmax) * s (soft=1) or
+ *          clamp(wfloor + (alpha >= 0), qmin, qmax) * s (soft=0). */
+int dpl_adaround_weight_f32(const float* d_wfloor, const float* d_alpha, const float* d_scale,
+                            int n_channels, uint64_t inner, float qmin, float qmax, int soft,
+                            float* d_wq, void* stream);
+
+/* One fused optimiser step on alpha given dL/dW_soft:
+ *   g = dW * s * h'(alpha) * [not clamped] + d/dalpha( reg_alpha * sum(1 - |2h-1|^beta) )
+ *   Adam(lr, b1, b2, eps, step) in place on (alpha, m, v).
+ * Also accumulates the regulariser value into d_reg (float64[1]) when non-NULL. */
+int dpl_adaround_step_f32(const float* d_grad_w, const float* d_wfloor, const float* d_scale,
+                          int n_channels, uint64_t inner, float qmin, float qmax, float beta,
+                          float reg_alpha, float lr, float b1, float b2, float eps, int step,
+                          float grad_scale, float* d_alpha, float* d_m, float* d_v,
+                          double* d_reg, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPL_B200_H_ */
