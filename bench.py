@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — the calibration hot path on BASELINE.json's headline configuration.
+
+    python bench.py --gpus N --steps K --warmup W            # ours (one rank per GPU)
+    python bench.py --impl reference --gpus N ...            # the CPU path beside it
+
+Workload (config.workload): ResNet-50, 1024 synthetic 3x224x224 images PER GPU,
+`-A hist --bins 2048 -D trt` (BASELINE.json configs[1]; at N GPUs the images are sharded
+by rank like configs[4], so per-GPU work is fixed = weak scaling).
+A "step" is one complete calibration job over the rank's 1024 images: pass 1 (forward +
+K1 range reduction), range all-reduce, pass 2 (forward + K2 histogram), histogram
+all-reduce, K3 percentile search -> clip ranges.
+
+  value  images/s, whole job over all ranks, images already resident in HBM
+  e2e    the same job through the plugin API (tensor_calibration) from PINNED HOST buffers:
+         every batch is copied host->device inside the timed region (both passes) and the
+         clip ranges are read back
+  roofline  the K2 histogram kernel: algorithmic bytes (4 B x elements of every blob of the
+         batch) / its mean launch duration, CUDA events on the launching stream, inside
+         the timed steps, against MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (torch-CPU fp32 forward + the reference's NumPy statistics,
+         one single-threaded worker per host core) on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "calibration images/sec (3x224x224), ResNet-50 -A hist --bins 2048"
+WORKLOAD = "ResNet-50 (BN-folded, 123 blobs, 106.39 MB/img), 1024 synthetic 3x224x224 images per GPU, -A hist --bins 2048 -D trt"
+IMAGES_PER_GPU = 1024
+BINS = 2048
+THRESHOLD = 0.99999
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=IMAGES_PER_GPU, help="images per GPU")
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--hist-variant", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active") and not val.lower().startswith("not"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------ CPU baseline
+def host_workers(cap=64):
+    """Host cores this process may use (cgroup / affinity aware), capped to bound memory."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, cap))
+
+
+def cpu_baseline(sample, procs=None):
+    """Oracle ("port") timed on host cores. Returns dict for the JSON line."""
+    from dipoorlet_b200 import workloads as W
+    from oracle import pipeline as P
+    procs = procs or host_workers()
+    if sample <= 0:
+        sample = 2 * procs   # two images per worker amortise the process start-up
+    sample = (sample // procs) * procs if sample >= procs else sample
+    model = W.build_resnet50(seed=0)
+    images = W.synthetic_images(sample, seed=0)
+    secs, done = P.timed_parallel(model, images, "hist", procs, BINS, THRESHOLD)
+    return {"value": done / secs, "unit": "images/s", "cores": min(procs, sample), "kind": "port",
+            "sample": f"{done} images of the same workload (-A hist: 2 fp32 forwards + np.histogram per "
+                      f"image), {min(procs, sample)} single-threaded worker processes, {secs:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (the oracle port:
+    /root/reference needs onnx + onnxruntime, not installable here) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    procs = host_workers()
+    sample = args.cpu_sample or 2 * procs
+    from dipoorlet_b200 import workloads as W
+    from oracle import pipeline as P
+    model = W.build_resnet50(seed=0)
+    images = W.synthetic_images(sample, seed=0)
+    for _ in range(min(args.warmup, 1)):
+        P.timed_parallel(model, images[:procs], "hist", procs, BINS, THRESHOLD)
+    total_t, total_n = 0.0, 0
+    for _ in range(args.steps):
+        secs, done = P.timed_parallel(model, images, "hist", procs, BINS, THRESHOLD)
+        total_t += secs
+        total_n += done
+    value = total_n / total_t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "bounded_sample_images_per_step": total_n // args.steps},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": min(procs, sample), "kind": "port",
+                             "sample": f"{total_n // args.steps} images per step, {min(procs, sample)} "
+                                       "single-threaded workers (torch-CPU fp32 forward + NumPy statistics)"},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from dipoorlet_b200 import dist_helper, forward_net as fwd, kernels as K, workloads as W
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.tensor_cali import tensor_calibration
+
+    rank, local_rank, world = dist_helper.init_from_env()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    n_img = args.images
+    model = W.build_resnet50(seed=0)
+    graph = ONNXGraph(model, "/tmp/dpl_bench", "trt")
+    # this rank's shard of the global image set (image idx is a function of (seed, idx))
+    images = W.synthetic_images(n_img, seed=0, start=rank * n_img)[:, 0]
+    host = fwd.ArrayInput({"input": images}, pin=True, start=rank * n_img)
+    dev_images = torch.from_numpy(images).to(dev)
+
+    class DeviceInput:  # images already resident in HBM (`value`)
+        def fetch(self, name, st, ed, shape):
+            lo = st - rank * n_img
+            return dev_images[lo:lo + (ed - st)]
+
+    def mk_args(source):
+        return make_args(input_dir=source, data_num=n_img * world, deploy="trt", act_quant="hist",
+                         bins=BINS, threshold=THRESHOLD, output_dir="/tmp/dpl_bench",
+                         calib_bs=args.batch, rank=rank, local_rank=local_rank, world_size=world)
+
+    hist_events = []
+
+    def job(source, timed_hist=False):
+        a = mk_args(source)
+        sess = fwd.CalibrationSession(graph, a, engine=job.engine)
+        job.engine = sess.engine
+        sess.run_minmax()
+        if timed_hist:
+            sess.hist_events = hist_events
+        sess.run_hist(BINS, args.hist_variant)
+        clip, sel = sess.percentile_clip(BINS, THRESHOLD)
+        return sess, clip
+
+    job.engine = None
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- value: images resident in HBM ------------------------------------------------
+    for _ in range(args.warmup):
+        job(DeviceInput())
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = K.launches()
+    t0 = time.time()
+    ms = timed(lambda: job(DeviceInput(), timed_hist=True), args.steps)
+    t1 = time.time()
+    launches = K.launches() - l0
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    value = n_img * world * args.steps / (ms / 1e3)
+
+    # K2 launch durations (events recorded on the launching stream inside the timed steps)
+    hist_ms = [a.elapsed_time(b) for a, b, _ in hist_events]
+    hist_bytes = [nb for _, _, nb in hist_events]
+    peak, peak_kind = measured_peak()
+    achieved = (sum(hist_bytes) / 1e9) / (sum(hist_ms) / 1e3) if hist_ms else 0.0
+
+    # ---- e2e: plugin API from pinned host buffers -----------------------------------------
+    d2h = {"n": 0}
+
+    def e2e_job():
+        a = mk_args(host)
+        a.act_quant = "hist"
+        fwd._SESSIONS.clear()
+        act, weight = tensor_calibration(graph, a)   # host dict of np.float32 clip values
+        d2h["n"] = 8 * len(act)
+        return act
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_job()
+    ms_e2e = timed(e2e_job, args.steps)
+    e2e_value = n_img * world * args.steps / (ms_e2e / 1e3)
+    h2d_per_step = 2 * images.nbytes * world  # both passes re-send the images
+
+    if rank != 0:
+        return
+    elems_per_img = W.blob_elements(W.resnet50_blob_shapes())
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "images_per_gpu": n_img, "forward_batch": args.batch,
+                   "l2": "inputs larger than L2: every timed kernel streams a %.1f GB batch of blobs "
+                         "(126 MB L2)" % (4 * elems_per_img * args.batch / 1e9),
+                   "forward": "torch/cuDNN fp32 (TF32 off) stand-in producer; statistics = libdpl_b200.so"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_per_step,
+                "d2h_bytes_per_step": d2h["n"], "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "K2 dpl_hist_abs_f32 variant %d" % args.hist_variant, "achieved": achieved, "peak": peak,
+                     "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured"
+                     else "fallback 6.65 TB/s", "unit": "GB/s", "frac": achieved / peak if peak else None,
+                     "traffic": None, "launches_timed": len(hist_ms),
+                     "bytes_per_launch": float(np.mean(hist_bytes)) if hist_bytes else 0,
+                     "ms_per_launch": float(np.mean(hist_ms)) if hist_ms else None},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
+        except Exception as e:  # the baseline must not take the measurement down
+            line["cpu_baseline"] = {"error": repr(e)}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

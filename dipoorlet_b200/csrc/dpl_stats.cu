@@ -366,6 +366,279 @@ hist_lanecol_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_t n_
   }
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- variants 4/5/6: lane-column histogram, tuned inner loop -----------------
+// Same idea as variant 1 with a cheaper per-element path (variant 1 issues ~23 SASS
+// instructions per element and is issue-bound at 68% of HBM peak):
+//   * word w holds bins w (low 16 bits) and w + nwords (high 16 bits): the word index is
+//     a mask / compare instead of shift + parity logic;
+//   * the edge correction is an integer mask from `set.lt` folded into one add;
+//   * out-of-range elements (NumPy's keep mask) are steered to a trash row instead of
+//     branching around the atomic; the atomic is a `red.shared` on a 32-bit shared address;
+//   * full iterations run without per-load predicates; the ragged end is a separate loop.
+template <bool POW2>
+__device__ __forceinline__ void lc2_add(uint32_t lane_base, float x, const BinParams& bp,
+                                        uint32_t nwords, uint32_t trash_addr) {
+  const float a = fabsf(x);
+  const float tm = __fmaf_rn(a, bp.inv_step, 8388608.0f);
+  const float rf = __fadd_rn(tm, -8388608.0f);
+  const float e0 = __fmul_rn(rf, bp.step);
+  int mask;
+  asm("set.lt.s32.f32 %0, %1, %2;" : "=r"(mask) : "f"(a), "f"(e0));  // -1 when |x| < edge(r)
+  uint32_t r = (uint32_t)(__float_as_int(tm) + mask - 0x4B000000);
+  r = min(r, (uint32_t)bp.last_bin);
+  const bool hi = r >= nwords;
+  const uint32_t w = POW2 ? (r & (nwords - 1u)) : (hi ? r - nwords : r);
+  uint32_t addr = lane_base + w * 128u;
+  addr = (a <= bp.dm) ? addr : trash_addr;
+  const uint32_t inc = hi ? 65536u : 1u;
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(inc) : "memory");
+}
+
+__device__ __forceinline__ void lc2_flush(uint32_t* sh, int nwords, int bins,
+                                          unsigned long long* __restrict__ g) {
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int w = warp; w < nwords; w += kHistWarps) {
+    const uint32_t v = sh[(w << 5) + lane];
+    sh[(w << 5) + lane] = 0;
+    const uint32_t lo = __reduce_add_sync(0xffffffffu, v & 0xffffu);
+    const uint32_t hi = __reduce_add_sync(0xffffffffu, v >> 16);
+    if (lane == 0 && lo) atomicAdd(g + w, (unsigned long long)lo);
+    if (lane == 1 && hi && w + nwords < bins) atomicAdd(g + w + nwords, (unsigned long long)hi);
+  }
+  __syncthreads();
+}
+
+template <bool POW2>
+__device__ __forceinline__ void lc2_add4(uint32_t lane_base, const float4& v, const BinParams& bp,
+                                         uint32_t nwords, uint32_t trash) {
+  lc2_add<POW2>(lane_base, v.x, bp, nwords, trash);
+  lc2_add<POW2>(lane_base, v.y, bp, nwords, trash);
+  lc2_add<POW2>(lane_base, v.z, bp, nwords, trash);
+  lc2_add<POW2>(lane_base, v.w, bp, nwords, trash);
+}
+
+// PREFETCH: issue the next iteration's loads before binning the current registers.
+template <bool POW2, bool PREFETCH>
+__global__ void __launch_bounds__(kHistThreads, 1)
+hist_lc2_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_t n_tiles,
+                const float* __restrict__ data_max, int bins,
+                unsigned long long* __restrict__ counts) {
+  extern __shared__ __align__(128) uint32_t sh[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nwords = (bins + 1) >> 1;
+  for (int i = tid; i < (nwords + 1) * 32; i += kHistThreads) sh[i] = 0;  // + trash row
+  __syncthreads();
+  const uint32_t lane_base = smem_u32(sh) + lane * 4u;
+  const uint32_t trash = lane_base + (uint32_t)nwords * 128u;
+
+  uint64_t tile = n_tiles * blockIdx.x / gridDim.x;
+  const uint64_t tile_end = n_tiles * (blockIdx.x + 1ull) / gridDim.x;
+  if (tile >= tile_end) return;
+  int b = find_blob<5>(blobs, n_blobs, tile);
+
+  while (tile < tile_end) {
+    uint64_t blob_tile_end = (b + 1 < n_blobs) ? blobs[b + 1].flat_tile_begin : n_tiles;
+    if (tile >= blob_tile_end) {
+      ++b;
+      continue;
+    }
+    const uint64_t te = min(tile_end, blob_tile_end);
+    const uint64_t n_elems = blobs[b].n_seg * blobs[b].seg_len;
+    const uint64_t e0 = (tile - blobs[b].flat_tile_begin) * DPL_FLAT_TILE;
+    const uint64_t e1 = min(n_elems, (te - blobs[b].flat_tile_begin) * DPL_FLAT_TILE);
+    const float* p = reinterpret_cast<const float*>(blobs[b].ptr) + e0;
+    const uint64_t len = e1 - e0;
+    const int stat = (int)blobs[b].stat_index;
+    const BinParams bp = make_bin_params(data_max[stat], bins);
+    unsigned long long* g = counts + (uint64_t)stat * bins;
+    const bool usable = (bp.dm >= 0.f) && (bp.dm < INFINITY);
+
+    if (usable && bp.zero_bin >= 0) {
+      uint32_t z = 0;
+      for (uint64_t i = tid; i < len; i += kHistThreads) z += (fabsf(ldg_stream1(p + i)) == 0.f);
+      z = __reduce_add_sync(0xffffffffu, z);
+      if (lane == 0 && z) atomicAdd(g + bp.zero_bin, (unsigned long long)z);
+    } else if (usable) {
+      const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+      const uint64_t n4 = aligned ? (len >> 2) : 0;
+      const float4* p4 = reinterpret_cast<const float4*>(p);
+      constexpr uint64_t kStep = (uint64_t)kHistThreads * kHistUnroll;
+      const uint64_t full = n4 / kStep;  // iterations with every load in range
+      uint32_t iters = 0;
+      if (PREFETCH) {
+        float4 cur[kHistUnroll], nxt[kHistUnroll];
+        if (full > 0) {
+#pragma unroll
+          for (int u = 0; u < kHistUnroll; ++u) cur[u] = ldg_stream4(p4 + (uint64_t)u * kHistThreads + tid);
+        }
+        for (uint64_t it = 0; it < full; ++it) {
+          if (it + 1 < full) {
+            const float4* q = p4 + (it + 1) * kStep + tid;
+#pragma unroll
+            for (int u = 0; u < kHistUnroll; ++u) nxt[u] = ldg_stream4(q + (uint64_t)u * kHistThreads);
+          }
+#pragma unroll
+          for (int u = 0; u < kHistUnroll; ++u) lc2_add4<POW2>(lane_base, cur[u], bp, nwords, trash);
+#pragma unroll
+          for (int u = 0; u < kHistUnroll; ++u) cur[u] = nxt[u];
+          if (++iters == kFlushIters) {
+            lc2_flush(sh, nwords, bins, g);
+            iters = 0;
+          }
+        }
+      } else {
+        for (uint64_t it = 0; it < full; ++it) {
+          const float4* q = p4 + it * kStep + tid;
+          float4 v[kHistUnroll];
+#pragma unroll
+          for (int u = 0; u < kHistUnroll; ++u) v[u] = ldg_stream4(q + (uint64_t)u * kHistThreads);
+#pragma unroll
+          for (int u = 0; u < kHistUnroll; ++u) lc2_add4<POW2>(lane_base, v[u], bp, nwords, trash);
+          if (++iters == kFlushIters) {
+            lc2_flush(sh, nwords, bins, g);
+            iters = 0;
+          }
+        }
+      }
+      // ragged end of the vector body: < kStep float4, at most kHistUnroll per thread
+      for (uint64_t i = full * kStep + tid; i < n4; i += kHistThreads)
+        lc2_add4<POW2>(lane_base, ldg_stream4(p4 + i), bp, nwords, trash);
+      // (iters < kFlushIters and this adds <= 16 per thread: still below 2^16 per column
+      //  because kFlushIters * kColPerIter + kColPerIter <= 65535 + 512 would overflow, so flush)
+      lc2_flush(sh, nwords, bins, g);
+      // scalar remainder, uniform trip count
+      const uint64_t rem0 = n4 << 2;
+      const uint64_t trips = (len - rem0 + kHistThreads - 1) / kHistThreads;
+      uint32_t sc = 0;
+      for (uint64_t j = 0; j < trips; ++j) {
+        const uint64_t i = rem0 + j * kHistThreads + tid;
+        if (i < len) lc2_add<POW2>(lane_base, ldg_stream1(p + i), bp, nwords, trash);
+        if (++sc == 2047u) {
+          lc2_flush(sh, nwords, bins, g);
+          sc = 0;
+        }
+      }
+      if (trips) lc2_flush(sh, nwords, bins, g);
+    }
+    tile = te;
+    ++b;
+  }
+}
+
+// ---- variant 7: half-warp columns, 32-bit counters ------------------------------
+// word bin * 16 + (lane & 15): lanes l and l + 16 share a column, so a warp's atomic sees
+// at most a 2-way bank conflict, but the counters are full 32-bit (no packing logic, no
+// periodic flush) and the per-element path is 3 instructions shorter than variant 4.
+__device__ __forceinline__ void lc3_add(uint32_t col_base, float x, const BinParams& bp,
+                                        uint32_t trash_addr) {
+  const float a = fabsf(x);
+  const float tm = __fmaf_rn(a, bp.inv_step, 8388608.0f);
+  const float rf = __fadd_rn(tm, -8388608.0f);
+  const float e0 = __fmul_rn(rf, bp.step);
+  int mask;
+  asm("set.lt.s32.f32 %0, %1, %2;" : "=r"(mask) : "f"(a), "f"(e0));
+  uint32_t r = (uint32_t)(__float_as_int(tm) + mask - 0x4B000000);
+  r = min(r, (uint32_t)bp.last_bin);
+  uint32_t addr = col_base + r * 64u;
+  addr = (a <= bp.dm) ? addr : trash_addr;
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u) : "memory");
+}
+
+__device__ __forceinline__ void lc3_flush(uint32_t* sh, int bins, unsigned long long* __restrict__ g) {
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b0 = warp * 2; b0 < bins; b0 += kHistWarps * 2) {
+    const int b = b0 + (lane >> 4);
+    uint32_t v = 0;
+    if (b < bins) {
+      v = sh[(b << 4) + (lane & 15)];
+      sh[(b << 4) + (lane & 15)] = 0;
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((lane & 15) == 0 && v && b < bins) atomicAdd(g + b, (unsigned long long)v);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kHistThreads, 1)
+hist_lc3_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_t n_tiles,
+                const float* __restrict__ data_max, int bins,
+                unsigned long long* __restrict__ counts) {
+  extern __shared__ __align__(128) uint32_t sh[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < (bins + 1) * 16; i += kHistThreads) sh[i] = 0;
+  __syncthreads();
+  const uint32_t col_base = smem_u32(sh) + (lane & 15) * 4u;
+  const uint32_t trash = col_base + (uint32_t)bins * 64u;
+
+  uint64_t tile = n_tiles * blockIdx.x / gridDim.x;
+  const uint64_t tile_end = n_tiles * (blockIdx.x + 1ull) / gridDim.x;
+  if (tile >= tile_end) return;
+  int b = find_blob<5>(blobs, n_blobs, tile);
+
+  while (tile < tile_end) {
+    uint64_t blob_tile_end = (b + 1 < n_blobs) ? blobs[b + 1].flat_tile_begin : n_tiles;
+    if (tile >= blob_tile_end) {
+      ++b;
+      continue;
+    }
+    const uint64_t te = min(tile_end, blob_tile_end);
+    const uint64_t n_elems = blobs[b].n_seg * blobs[b].seg_len;
+    const uint64_t e0 = (tile - blobs[b].flat_tile_begin) * DPL_FLAT_TILE;
+    const uint64_t e1 = min(n_elems, (te - blobs[b].flat_tile_begin) * DPL_FLAT_TILE);
+    const float* p = reinterpret_cast<const float*>(blobs[b].ptr) + e0;
+    const uint64_t len = e1 - e0;
+    const int stat = (int)blobs[b].stat_index;
+    const BinParams bp = make_bin_params(data_max[stat], bins);
+    unsigned long long* g = counts + (uint64_t)stat * bins;
+    const bool usable = (bp.dm >= 0.f) && (bp.dm < INFINITY);
+
+    if (usable && bp.zero_bin >= 0) {
+      uint32_t z = 0;
+      for (uint64_t i = tid; i < len; i += kHistThreads) z += (fabsf(ldg_stream1(p + i)) == 0.f);
+      z = __reduce_add_sync(0xffffffffu, z);
+      if (lane == 0 && z) atomicAdd(g + bp.zero_bin, (unsigned long long)z);
+    } else if (usable) {
+      const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+      const uint64_t n4 = aligned ? (len >> 2) : 0;
+      const float4* p4 = reinterpret_cast<const float4*>(p);
+      constexpr uint64_t kStep = (uint64_t)kHistThreads * kHistUnroll;
+      const uint64_t full = n4 / kStep;
+      for (uint64_t it = 0; it < full; ++it) {
+        const float4* q = p4 + it * kStep + tid;
+        float4 v[kHistUnroll];
+#pragma unroll
+        for (int u = 0; u < kHistUnroll; ++u) v[u] = ldg_stream4(q + (uint64_t)u * kHistThreads);
+#pragma unroll
+        for (int u = 0; u < kHistUnroll; ++u) {
+          lc3_add(col_base, v[u].x, bp, trash);
+          lc3_add(col_base, v[u].y, bp, trash);
+          lc3_add(col_base, v[u].z, bp, trash);
+          lc3_add(col_base, v[u].w, bp, trash);
+        }
+      }
+      for (uint64_t i = full * kStep + tid; i < n4; i += kHistThreads) {
+        const float4 v = ldg_stream4(p4 + i);
+        lc3_add(col_base, v.x, bp, trash);
+        lc3_add(col_base, v.y, bp, trash);
+        lc3_add(col_base, v.z, bp, trash);
+        lc3_add(col_base, v.w, bp, trash);
+      }
+      for (uint64_t i = (n4 << 2) + tid; i < len; i += kHistThreads)
+        lc3_add(col_base, ldg_stream1(p + i), bp, trash);
+      lc3_flush(sh, bins, g);  // one CTA's share of a blob is far below 2^32 elements
+    }
+    tile = te;
+    ++b;
+  }
+}
+
 // ---- variant 3: lane-column histogram fed by a TMA-staged tile ring ---------
 // Same counters as variant 1; the blob is streamed into a shared-memory ring with 1-D
 // bulk async copies (cp.async.bulk, SASS UBLKCP) completing on mbarriers, so no load
@@ -373,9 +646,6 @@ hist_lanecol_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_t n_
 constexpr int kStageFloats = 8192;  // 32 KB per stage: 2 float4 per thread
 constexpr int kStageBytes = kStageFloats * 4;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -414,8 +684,8 @@ hist_lanecol_tma_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_
   __shared__ __align__(8) uint64_t s_full[4], s_empty[4];
   const int tid = threadIdx.x, lane = tid & 31;
   const int nwords = (bins + 1) >> 1;
-  float* ring = reinterpret_cast<float*>(sh + (size_t)nwords * 32);
-  for (int i = tid; i < nwords * 32; i += kHistThreads) sh[i] = 0;
+  float* ring = reinterpret_cast<float*>(sh + (size_t)(nwords + 1) * 32);  // after the trash row
+  for (int i = tid; i < (nwords + 1) * 32; i += kHistThreads) sh[i] = 0;
   if (tid == 0) {
     for (int s = 0; s < n_stages; ++s) {
       mbar_init(smem_u32(&s_full[s]), 1);
@@ -424,7 +694,8 @@ hist_lanecol_tma_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  uint32_t* sh_lane = sh + lane;
+  const uint32_t lane_base = smem_u32(sh) + lane * 4u;
+  const uint32_t trash = lane_base + (uint32_t)nwords * 128u;
 
   uint64_t tile = n_tiles * blockIdx.x / gridDim.x;
   const uint64_t tile_end = n_tiles * (blockIdx.x + 1ull) / gridDim.x;
@@ -494,19 +765,19 @@ hist_lanecol_tma_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_
                    p + (size_t)(c + n_stages) * kStageFloats, bytes, smem_u32(&s_full[s]));
         }
         if (ok0) {
-          lanecol_add(sh_lane, bin_of(v0.x, bp));
-          lanecol_add(sh_lane, bin_of(v0.y, bp));
-          lanecol_add(sh_lane, bin_of(v0.z, bp));
-          lanecol_add(sh_lane, bin_of(v0.w, bp));
+          lc2_add<false>(lane_base, v0.x, bp, nwords, trash);
+          lc2_add<false>(lane_base, v0.y, bp, nwords, trash);
+          lc2_add<false>(lane_base, v0.z, bp, nwords, trash);
+          lc2_add<false>(lane_base, v0.w, bp, nwords, trash);
         }
         if (ok1) {
-          lanecol_add(sh_lane, bin_of(v1.x, bp));
-          lanecol_add(sh_lane, bin_of(v1.y, bp));
-          lanecol_add(sh_lane, bin_of(v1.z, bp));
-          lanecol_add(sh_lane, bin_of(v1.w, bp));
+          lc2_add<false>(lane_base, v1.x, bp, nwords, trash);
+          lc2_add<false>(lane_base, v1.y, bp, nwords, trash);
+          lc2_add<false>(lane_base, v1.z, bp, nwords, trash);
+          lc2_add<false>(lane_base, v1.w, bp, nwords, trash);
         }
         if (++since_flush == 255u) {  // 255 chunks * 256 elements per lane column < 2^16
-          lanecol_flush(sh, nwords, bins, g);
+          lc2_flush(sh, nwords, bins, g);
           since_flush = 0;
         }
       }
@@ -518,13 +789,13 @@ hist_lanecol_tma_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_
       uint32_t sc = 0;
       for (uint64_t j = 0; j < trips; ++j) {
         const uint64_t i = rem0 + j * kHistThreads + tid;
-        if (i < len) lanecol_add(sh_lane, bin_of(ldg_stream1(p + i), bp));
+        if (i < len) lc2_add<false>(lane_base, ldg_stream1(p + i), bp, nwords, trash);
         if (++sc == 2047u) {
-          lanecol_flush(sh, nwords, bins, g);
+          lc2_flush(sh, nwords, bins, g);
           sc = 0;
         }
       }
-      lanecol_flush(sh, nwords, bins, g);
+      lc2_flush(sh, nwords, bins, g);
     }
     tile = te;
     ++b;
@@ -792,9 +1063,41 @@ extern "C" int dpl_hist_abs_f32(const dpl_blob* d_blobs, int n_blobs, uint64_t n
     DPL_LAUNCH_CHECK("hist_lanecol_kernel");
     return 0;
   }
+  if (variant == 4 || variant == 5) {
+    DPL_REQUIRE(bins <= kLaneColMaxBins, "lane-column variant supports bins <= 3072");
+    const int nwords = (bins + 1) >> 1;
+    const size_t smem = (size_t)(nwords + 1) * 128;
+    const bool pow2 = (nwords & (nwords - 1)) == 0 && (bins & 1) == 0;
+    auto kern = pow2 ? (variant == 5 ? hist_lc2_kernel<true, true> : hist_lc2_kernel<true, false>)
+                     : (variant == 5 ? hist_lc2_kernel<false, true> : hist_lc2_kernel<false, false>);
+    int s = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (kLaneColMaxBins / 2 + 1) * 128),
+                        "cudaFuncSetAttribute(hist_lc2_kernel)");
+    if (s) return s;
+    uint64_t grid = (uint64_t)sm_count();
+    if (grid > n_flat_tiles) grid = n_flat_tiles;
+    kern<<<(unsigned)grid, kHistThreads, smem, st>>>(d_blobs, n_blobs, n_flat_tiles, d_data_max, bins,
+                                                     d_counts);
+    DPL_LAUNCH_CHECK("hist_lc2_kernel");
+    return 0;
+  }
+  if (variant == 7) {
+    DPL_REQUIRE(bins <= kLaneColMaxBins, "half-warp-column variant supports bins <= 3072");
+    const size_t smem = (size_t)(bins + 1) * 64;
+    int s = cuda_status(cudaFuncSetAttribute(hist_lc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (kLaneColMaxBins + 1) * 64),
+                        "cudaFuncSetAttribute(hist_lc3_kernel)");
+    if (s) return s;
+    uint64_t grid = (uint64_t)sm_count();
+    if (grid > n_flat_tiles) grid = n_flat_tiles;
+    hist_lc3_kernel<<<(unsigned)grid, kHistThreads, smem, st>>>(d_blobs, n_blobs, n_flat_tiles,
+                                                                d_data_max, bins, d_counts);
+    DPL_LAUNCH_CHECK("hist_lc3_kernel");
+    return 0;
+  }
   if (variant == 3) {
-    DPL_REQUIRE(bins <= 2048, "TMA lane-column variant supports bins <= 2048");
-    const size_t hist_bytes = (size_t)((bins + 1) >> 1) * 128;
+    DPL_REQUIRE(bins <= 2048, "TMA lane-column variant supports bins <= 2048 (ring + histogram share 227 KB)");
+    const size_t hist_bytes = (size_t)(((bins + 1) >> 1) + 1) * 128;
     const int n_stages = 3;
     const size_t smem = hist_bytes + (size_t)n_stages * kStageBytes;
     int s = cuda_status(cudaFuncSetAttribute(hist_lanecol_tma_kernel,

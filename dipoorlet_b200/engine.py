@@ -1,0 +1,259 @@
+"""Batched blob producer: executes the (fp32 or Q/DQ) graph on the GPU for a whole batch
+of calibration images and leaves every requested activation blob resident in HBM, where
+the statistics kernels consume it in place.
+
+Replaces the reference's per-sample `ort.InferenceSession.run` with every node output
+promoted to a graph output and copied back to the host (dipoorlet/forward_net.py:195-216)
+and the per-node sessions of ActivationCache.forward_subnet (forward_net.py:81-128).
+
+STAND-IN NOTICE: the dense operators (Conv / Gemm / pooling)
+are issued through torch's CUDA ops (cuDNN / cuBLAS, true fp32: TF32 disabled), i.e. a
+library call playing the role onnxruntime's CUDA EP plays in the reference. The statistics,
+fake-quant and rounding kernels — the hot path this repo is about — are libdpl_b200.so.
+QuantizeLinear + DequantizeLinear pairs are executed as ONE fused K5 launch.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import kernels as K
+
+QDQ = ("QuantizeLinear", "DequantizeLinear")
+
+
+def _sym_pads(pads, nd):
+    lo, hi = list(pads[:nd]), list(pads[nd:])
+    return lo == hi, lo, hi
+
+
+class Engine:
+    def __init__(self, onnx_graph, device=None, allow_tf32=False, _unit_test_cpu=False):
+        self.g = onnx_graph
+        self.device = torch.device(device if device is not None else "cuda")
+        # `_unit_test_cpu` lets tests/ check the operator interpreter against the oracle on a
+        # box without a GPU; no product entry point sets it, and Q/DQ (K5) still needs CUDA.
+        if self.device.type != "cuda" and not _unit_test_cpu:
+            raise RuntimeError("dipoorlet_b200.engine.Engine runs on a CUDA device only "
+                               "(no CPU fallback on the product path)")
+        self.allow_tf32 = allow_tf32
+        self.params = {}
+        self.zero_points = {}
+        self.refresh_initializers()
+        self.nodes = list(onnx_graph.model.graph.nodes)
+        self._fused_q = set()
+
+    def refresh_initializers(self, names=None):
+        """(Re)upload initializers — after bias correction / rounding rewrote weights."""
+        inits = self.g.model.graph.initializers
+        for name in (names if names is not None else inits):
+            arr = inits[name]
+            if arr.dtype == np.float64:
+                arr = arr.astype(np.float32)
+            self.params[name] = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+            if arr.dtype in (np.int8, np.uint8):  # zero points: K5 takes int32
+                self.zero_points[name] = (self.params[name].reshape(-1).to(torch.int32).contiguous(),
+                                          arr.dtype == np.uint8)
+
+    # ------------------------------------------------------------------ execution
+    def blob_names(self):
+        """Names in the order the reference's statistics dicts are filled
+        (forward_net.py:195-198,220-235): network inputs, then every node output in node
+        order with the original network outputs moved to the end."""
+        outs = [o for n in self.nodes for o in n.output if o and o not in self.g.network_outputs]
+        return list(self.g.network_inputs) + outs + list(self.g.network_outputs)
+
+    def run(self, feeds, want="all", start_after=None, cache=None):
+        """feeds: name -> [B, ...] float32 CUDA tensor. Returns OrderedDict name -> tensor
+        for `want` ('all' = every blob of blob_names(), or an iterable of names).
+        `cache` (dict) is consulted before computing a tensor and is not modified."""
+        torch.backends.cudnn.allow_tf32 = self.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.allow_tf32
+        env = dict(feeds)
+        if cache:
+            for k, v in cache.items():
+                env.setdefault(k, v)
+        want_all = isinstance(want, str) and want == "all"
+        wanted = None if want_all else set(want)
+        need = None
+        if not want_all:
+            need = self._needed_nodes(wanted, env)
+        remaining = {}
+        if not want_all:
+            for i in need:
+                for t in self.nodes[i].input:
+                    remaining[t] = remaining.get(t, 0) + 1
+        with torch.no_grad():
+            for i, node in enumerate(self.nodes):
+                if need is not None and i not in need:
+                    continue
+                if all(o in env for o in node.output if o):
+                    continue
+                outs = self._exec(node, env)
+                for o, v in zip(node.output, outs):
+                    if o:
+                        env[o] = v
+                if not want_all:
+                    for t in node.input:
+                        if t in remaining:
+                            remaining[t] -= 1
+                            if remaining[t] == 0 and t not in wanted and t not in feeds \
+                                    and not (cache and t in cache):
+                                env.pop(t, None)
+        names = self.blob_names() if want_all else [w for w in want]
+        return OrderedDict((n, env[n]) for n in names if n in env)
+
+    def _needed_nodes(self, wanted, env):
+        need, stack = set(), [w for w in wanted if w not in env]
+        while stack:
+            t = stack.pop()
+            prod = self.g.output_map.get(t)
+            if prod is None:
+                if t not in self.params and t not in env and t != "":
+                    raise KeyError(f"tensor {t!r} has no producer and was not fed")
+                continue
+            idx = self.g.name_idx_map[prod.name]
+            if idx in need:
+                continue
+            need.add(idx)
+            for i in prod.input:
+                if i and i not in env and i not in self.params:
+                    stack.append(i)
+        return need
+
+    def _val(self, name, env):
+        if name in env:
+            return env[name]
+        return self.params[name]
+
+    def _host(self, name, env):
+        """Small constant operands (Clip bounds, Reshape targets) read on the host without
+        a device sync when they are initializers."""
+        arr = self.g.model.graph.initializers.get(name)
+        return arr if arr is not None else self._val(name, env).cpu().numpy()
+
+    def _exec(self, node, env):
+        op, a = node.op_type, node.attrs
+        x = self._val(node.input[0], env) if node.input and node.input[0] else None
+        if op == "Conv":
+            w = self._val(node.input[1], env)
+            b = self._val(node.input[2], env) if len(node.input) > 2 and node.input[2] else None
+            nd = w.dim() - 2
+            stride = a.get("strides", [1] * nd)
+            dil = a.get("dilations", [1] * nd)
+            sym, lo, hi = _sym_pads(a.get("pads", [0] * (2 * nd)), nd)
+            if not sym:
+                x = F.pad(x, [p for i in reversed(range(nd)) for p in (lo[i], hi[i])])
+                lo = [0] * nd
+            fn = F.conv2d if nd == 2 else (F.conv1d if nd == 1 else F.conv3d)
+            return [fn(x, w, b, stride, lo, dil, a.get("group", 1))]
+        if op == "ConvTranspose":
+            w = self._val(node.input[1], env)
+            b = self._val(node.input[2], env) if len(node.input) > 2 and node.input[2] else None
+            nd = w.dim() - 2
+            pads = a.get("pads", [0] * (2 * nd))
+            return [F.conv_transpose2d(x, w, b, a.get("strides", [1] * nd), pads[:nd],
+                                       a.get("output_padding", [0] * nd), a.get("group", 1),
+                                       a.get("dilations", [1] * nd))]
+        if op == "Relu":
+            return [torch.relu(x)]
+        if op == "Clip":
+            lo = a.get("min")
+            hi = a.get("max")
+            if len(node.input) > 1 and node.input[1]:
+                lo = float(self._host(node.input[1], env).reshape(-1)[0])
+            if len(node.input) > 2 and node.input[2]:
+                hi = float(self._host(node.input[2], env).reshape(-1)[0])
+            return [torch.clamp(x, lo, hi)]
+        if op in ("MaxPool", "AveragePool"):
+            nd = x.dim() - 2
+            k = a["kernel_shape"]
+            stride = a.get("strides", [1] * nd)
+            sym, lo, hi = _sym_pads(a.get("pads", [0] * (2 * nd)), nd)
+            ceil_mode = bool(a.get("ceil_mode", 0))
+            if op == "MaxPool":
+                if not sym:
+                    x = F.pad(x, [p for i in reversed(range(nd)) for p in (lo[i], hi[i])],
+                              value=float("-inf"))
+                    lo = [0] * nd
+                return [F.max_pool2d(x, k, stride, lo, a.get("dilations", [1] * nd), ceil_mode)]
+            if not sym:
+                raise NotImplementedError("AveragePool with asymmetric pads")
+            return [F.avg_pool2d(x, k, stride, lo, ceil_mode, bool(a.get("count_include_pad", 0)))]
+        if op == "GlobalAveragePool":
+            return [x.mean(dim=tuple(range(2, x.dim())), keepdim=True)]
+        if op in ("Add", "Sub", "Mul", "Div"):
+            y = self._val(node.input[1], env)
+            return [{"Add": torch.add, "Sub": torch.sub, "Mul": torch.mul, "Div": torch.div}[op](x, y)]
+        if op == "Flatten":
+            ax = a.get("axis", 1)
+            return [x.flatten(ax) if ax > 0 else x.reshape(1, -1)]
+        if op == "Gemm":
+            w = self._val(node.input[1], env)
+            c = self._val(node.input[2], env) if len(node.input) > 2 and node.input[2] else None
+            alpha, beta = a.get("alpha", 1.0), a.get("beta", 1.0)
+            if a.get("transA", 0):
+                x = x.t()
+            if alpha == 1.0 and beta == 1.0 and a.get("transB", 0) and (c is None or c.dim() == 1):
+                return [F.linear(x, w, c)]
+            y = alpha * (x @ (w.t() if a.get("transB", 0) else w))
+            return [y if c is None else y + beta * c]
+        if op == "MatMul":
+            return [x @ self._val(node.input[1], env)]
+        if op == "Reshape":
+            tgt = [int(v) for v in self._host(node.input[1], env).reshape(-1)]
+            declared = self.g.tensor_name_shape_map.get(node.input[0])
+            if declared and tgt and declared[0] == tgt[0] and x.shape[0] != declared[0]:
+                tgt[0] = x.shape[0]  # the leading dim is the image index
+            tgt = [x.shape[i] if v == 0 else v for i, v in enumerate(tgt)]
+            return [x.reshape(tgt)]
+        if op == "Sigmoid":
+            return [torch.sigmoid(x)]
+        if op == "Identity" or op == "Dropout":
+            return [x]
+        if op == "Concat":
+            return [torch.cat([self._val(i, env) for i in node.input], a["axis"])]
+        if op == "Transpose":
+            return [x.permute(a.get("perm", list(range(x.dim()))[::-1])).contiguous()]
+        if op == "LeakyRelu":
+            return [F.leaky_relu(x, a.get("alpha", 0.01))]
+        if op == "PRelu":
+            slope = self._val(node.input[1], env)
+            return [torch.where(x >= 0, x, x * slope)]
+        if op == "HardSigmoid":
+            return [torch.clamp(a.get("alpha", 0.2) * x + a.get("beta", 0.5), 0, 1)]
+        if op == "Softmax":
+            return [torch.softmax(x, a.get("axis", -1))]
+        if op == "ReduceMean":
+            return [x.mean(dim=a.get("axes"), keepdim=bool(a.get("keepdims", 1)))]
+        if op == "BatchNormalization":
+            s, b, m, v = (self._val(i, env) for i in node.input[1:5])
+            return [F.batch_norm(x, m, v, s, b, False, 0.0, a.get("epsilon", 1e-5))]
+        if op == "QuantizeLinear":
+            return [self._quantize(node, x, env)]
+        if op == "DequantizeLinear":
+            if node.input[0] in self._fused_q:
+                return [x]  # K5 already produced the dequantised values
+            scale = self._val(node.input[1], env)
+            zp = self._val(node.input[2], env).float() if len(node.input) > 2 else 0.
+            if scale.numel() > 1:
+                shape = [1] * x.dim()
+                shape[a.get("axis", 1)] = -1
+                scale, zp = scale.reshape(shape), (zp.reshape(shape) if torch.is_tensor(zp) else zp)
+            return [(x.float() - zp) * scale]
+        raise NotImplementedError(f"engine: unsupported op {op} ({node.name})")
+
+    def _quantize(self, node, x, env):
+        """QuantizeLinear immediately undone by its DequantizeLinear (the only pattern
+        quant_graph emits, quantize.py:209-231): one fused K5 pass; the `_q` tensor holds
+        the already-dequantised float values."""
+        scale = self._val(node.input[1], env).reshape(-1)
+        zp, unsigned = None, False
+        if len(node.input) > 2 and node.input[2]:
+            zp, unsigned = self.zero_points[node.input[2]]
+        qlo, qhi = (0, 255) if unsigned else (-128, 127)
+        axis = node.attrs.get("axis", 1) if scale.numel() > 1 else None
+        x = x if x.is_contiguous() else x.contiguous()
+        self._fused_q.add(node.output[0])
+        return K.fakequant(x, scale, zp, qlo, qhi, axis=axis)

@@ -1,0 +1,314 @@
+"""Calibration forward passes on the GPU — the B200 replacement of
+dipoorlet/forward_net.py.
+
+The reference runs ONNXRuntime one image at a time, copies every node output (106 MB per
+ResNet-50 image) back to the host and reduces it with single-threaded NumPy. Here a
+`CalibrationSession` pushes a batch of images through the graph (`engine.Engine`), keeps
+all blobs of the batch in HBM and reduces them in place with ONE launch per statistic over
+the whole blob table (libdpl_b200.so: K1 segment stats, K2 histogram, K3 percentile, K4
+OCTAV). Statistics stay on the device between passes; only the final per-blob numbers
+(a few KB) travel to the host.
+
+The public functions keep the reference names, arguments and return shapes
+(forward_net.py:192-342): forward_get_minmax / forward_get_hist / forward_net_octav,
+ActivationCache, input_data_generator, forward_get_tensor.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import dist_helper
+from . import kernels as K
+from .engine import Engine
+from .platform_settings import platform_setting_table
+from .utils import logger
+
+
+# ------------------------------------------------------------------------ inputs
+def input_data_generator(input_dir, input_name_list, data_st_idx, data_ed_idx):
+    """Same files as the reference: {input_dir}/{name}/{idx}.bin raw float32
+    (forward_net.py:459-464)."""
+    for idx in range(data_st_idx, data_ed_idx):
+        yield {name: np.fromfile(f"{input_dir}/{name}/{idx}.bin", "float32")
+               for name in input_name_list}
+
+
+class ArrayInput:
+    """In-memory calibration set: name -> float32 array [N, ...] (host, ideally pinned).
+    Accepted wherever the reference takes `args.input_dir`; lets bench.py time the whole
+    job from host buffers without going through the filesystem."""
+
+    def __init__(self, arrays, pin=True, start=0):
+        self.start = start  # global index of the first image held (a rank's shard)
+        self.tensors = {}
+        for name, arr in arrays.items():
+            t = arr if torch.is_tensor(arr) else torch.from_numpy(np.ascontiguousarray(arr))
+            if pin and torch.cuda.is_available() and not t.is_pinned():
+                t = t.pin_memory()
+            self.tensors[name] = t
+
+    def fetch(self, name, st, ed, shape):
+        t = self.tensors[name][st - self.start:ed - self.start]
+        return t.reshape((ed - st,) + tuple(shape))
+
+
+class FileInput:
+    def __init__(self, input_dir):
+        self.input_dir = input_dir
+
+    def fetch(self, name, st, ed, shape):
+        n = int(np.prod(shape))
+        buf = torch.empty((ed - st, n), dtype=torch.float32,
+                          pin_memory=torch.cuda.is_available())
+        view = buf.numpy()
+        for i, idx in enumerate(range(st, ed)):
+            view[i] = np.fromfile(f"{self.input_dir}/{name}/{idx}.bin", "float32")
+        return buf.reshape((ed - st,) + tuple(shape))
+
+
+def as_input_source(input_dir):
+    return input_dir if hasattr(input_dir, "fetch") else FileInput(input_dir)
+
+
+def _device_of(args):
+    """cuda:<local_rank>. `args._test_device` exists only so that tests/ can drive the host
+    logic with mocked kernels on a box without a GPU; the CLI never sets it."""
+    forced = getattr(args, "_test_device", None)
+    return torch.device(forced) if forced else torch.device("cuda", getattr(args, "local_rank", 0) or 0)
+
+
+def shard_range(args):
+    """forward_net.py:207-209: contiguous shard, floor division (the tail is dropped)."""
+    rank_num = args.data_num // args.world_size
+    st = args.rank * rank_num
+    return st, min((args.rank + 1) * rank_num, args.data_num)
+
+
+def _per_image_shape(onnx_graph, name):
+    shape = list(onnx_graph.get_tensor_shape(name))
+    if not shape or shape[0] not in (0, 1):
+        raise NotImplementedError(
+            f"network input {name!r} has leading dimension {shape[:1]}; the batched engine "
+            "needs models exported with batch 1 (as every BASELINE.json config is)")
+    return shape[1:]
+
+
+def default_batch(onnx_graph, engine, budget_bytes=6 << 30, cap=64):
+    per_img = 4 * sum(int(np.prod(onnx_graph.get_tensor_shape(n)[1:]))
+                      for n in engine.blob_names() if n in onnx_graph.tensor_name_shape_map)
+    return int(max(1, min(cap, budget_bytes // max(per_img, 1))))
+
+
+# ------------------------------------------------------------------------ session
+class CalibrationSession:
+    """Device-resident calibration statistics of one rank's image shard."""
+
+    def __init__(self, onnx_graph, args, engine=None):
+        self.g = onnx_graph
+        self.args = args
+        dev = _device_of(args)
+        self.device = dev
+        self.engine = engine or Engine(onnx_graph, dev, _unit_test_cpu=dev.type != "cuda")
+        self.names = self.engine.blob_names()
+        self.n_stats = len(self.names)
+        self.st, self.ed = shard_range(args)
+        self.n_local = self.ed - self.st
+        self.source = as_input_source(args.input_dir)
+        self.batch_size = int(getattr(args, "calib_bs", 0) or default_batch(onnx_graph, self.engine))
+        self.ws = K.Workspace(dev)
+        self.in_shapes = {n: _per_image_shape(onnx_graph, n) for n in onnx_graph.network_inputs}
+        self.h2d_bytes = 0
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.blob_min = torch.full((self.n_stats,), float("inf"), **f32)
+        self.blob_max = torch.full((self.n_stats,), float("-inf"), **f32)
+        self.seg_min = self.seg_max = self.seg_abssum = self.seg_nnz = self.seg_s = None
+        self.data_max = None
+        self.counts = None
+
+    def batches(self):
+        for b0 in range(self.st, self.ed, self.batch_size):
+            b1 = min(b0 + self.batch_size, self.ed)
+            feeds = {}
+            for name, shape in self.in_shapes.items():
+                host = self.source.fetch(name, b0, b1, shape)
+                self.h2d_bytes += host.numel() * 4
+                feeds[name] = host.to(self.device, non_blocking=True)
+            blobs = self.engine.run(feeds, want="all")
+            yield b0 - self.st, b1 - self.st, K.BlobBatch([blobs[n] for n in self.names])
+
+    # -- pass 1: min / max (+ moments for OCTAV) ------------------------------------
+    def run_minmax(self, moments=False, octav_k=None):
+        n, dev = self.n_local, self.device
+        self.seg_min = torch.empty((self.n_stats, n), dtype=torch.float32, device=dev)
+        self.seg_max = torch.empty((self.n_stats, n), dtype=torch.float32, device=dev)
+        if moments:
+            self.seg_abssum = torch.empty((self.n_stats, n), dtype=torch.float64, device=dev)
+            self.seg_nnz = torch.empty((self.n_stats, n), dtype=torch.int64, device=dev)
+        if octav_k is not None:
+            self.seg_s = torch.empty((self.n_stats, n), dtype=torch.float32, device=dev)
+        for lo, hi, batch in self.batches():
+            b = hi - lo
+            smin = torch.empty(self.n_stats * b, dtype=torch.float32, device=dev)
+            smax = torch.empty_like(smin)
+            ssum = torch.empty(self.n_stats * b, dtype=torch.float64, device=dev) if moments else None
+            snnz = torch.empty(self.n_stats * b, dtype=torch.int64, device=dev) if moments else None
+            K.segstats(batch, smin, smax, ssum, snnz, self.blob_min, self.blob_max, self.ws)
+            self.seg_min[:, lo:hi] = smin.view(self.n_stats, b)
+            self.seg_max[:, lo:hi] = smax.view(self.n_stats, b)
+            if moments:
+                self.seg_abssum[:, lo:hi] = ssum.view(self.n_stats, b)
+                self.seg_nnz[:, lo:hi] = snnz.view(self.n_stats, b)
+            if octav_k is not None:
+                s = torch.empty(self.n_stats * b, dtype=torch.float32, device=dev)
+                K.octav(batch, ssum, snnz, octav_k, s, workspace=self.ws)
+                self.seg_s[:, lo:hi] = s.view(self.n_stats, b)
+            del batch
+
+    # -- pass 2: histogram ------------------------------------------------------------
+    def run_hist(self, bins, variant=0):
+        dist_helper.allreduce_minmax(self.blob_min, self.blob_max)   # global range
+        self.data_max = torch.empty(self.n_stats, dtype=torch.float32, device=self.device)
+        K.absmax(self.blob_min, self.blob_max, self.data_max)
+        self.counts = torch.zeros((self.n_stats, int(bins)), dtype=torch.int64, device=self.device)
+        events = getattr(self, "hist_events", None)  # bench.py: per-launch CUDA-event timing
+        for lo, hi, batch in self.batches():
+            if events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            K.hist_abs(batch, self.data_max, self.counts, int(bins), variant)
+            if events is not None:
+                e1.record()
+                events.append((e0, e1, batch.elements * 4))
+            del batch
+        dist_helper.allreduce_sum(self.counts)
+
+    def percentile_clip(self, bins, threshold):
+        clip = torch.empty((self.n_stats, 2), dtype=torch.float32, device=self.device)
+        sel = torch.empty(self.n_stats, dtype=torch.int32, device=self.device)
+        K.hist_percentile(self.counts, int(bins), float(threshold), self.data_max, self.blob_min,
+                          self.blob_max, clip, sel)
+        return clip, sel
+
+    # -- host views in the reference's return shapes ------------------------------------
+    def minmax_dict(self):
+        mx, mn = self.seg_max.cpu().numpy(), self.seg_min.cpu().numpy()
+        return {name: {"max": mx[i], "min": mn[i]} for i, name in enumerate(self.names)}
+
+
+_SESSIONS = {}
+
+
+def _session(onnx_graph, args, fresh=False):
+    key = id(onnx_graph)
+    if fresh or key not in _SESSIONS:
+        _SESSIONS.clear()
+        _SESSIONS[key] = CalibrationSession(onnx_graph, args)
+    return _SESSIONS[key]
+
+
+def forward_get_minmax(onnx_graph, args):
+    """-> {name: {'max': float32[n_local], 'min': float32[n_local]}} (forward_net.py:192-237);
+    per-image values in image order, as arrays instead of lists of scalars."""
+    sess = _session(onnx_graph, args, fresh=True)
+    sess.run_minmax()
+    return sess.minmax_dict()
+
+
+def forward_get_hist(onnx_graph, stats_min_max, args):
+    """-> {name: [int64[bins]]}: the histogram of |x| over this job's images, already
+    summed over images (and ranks), in a one-element list so that the reference's
+    `np.stack(hist).sum(0)` (basic_algorithm.py:38) is the identity (forward_net.py:240-281)."""
+    sess = _session(onnx_graph, args)
+    if sess.seg_min is None:   # stats came from elsewhere (store_stats): seed the range
+        mn = np.array([np.min(stats_min_max[n]["min"]) for n in sess.names], np.float32)
+        mx = np.array([np.max(stats_min_max[n]["max"]) for n in sess.names], np.float32)
+        sess.blob_min.copy_(torch.from_numpy(mn))
+        sess.blob_max.copy_(torch.from_numpy(mx))
+    sess.run_hist(int(args.bins))
+    counts = sess.counts.cpu().numpy()
+    return {name: [counts[i]] for i, name in enumerate(sess.names)}
+
+
+def forward_net_octav(onnx_graph, args):
+    """-> {name: {'optimal_s': float32[n_local], 'min': ..., 'max': ...}} (forward_net.py:284-342)."""
+    sess = _session(onnx_graph, args, fresh=True)
+    if "dynamic_sym" in platform_setting_table[args.deploy]["qi_params"]:
+        raise NotImplementedError("'mse' calibration with a dynamic_sym platform (unsigned = 4 "
+                                  "per blob, forward_net.py:319-322) is outside the trt hot path")
+    sess.run_minmax(moments=True, octav_k=1 / (4 ** 8) / 3 / 1)
+    s, mx, mn = sess.seg_s.cpu().numpy(), sess.seg_max.cpu().numpy(), sess.seg_min.cpu().numpy()
+    return {name: {"optimal_s": s[i], "min": mn[i], "max": mx[i]} for i, name in enumerate(sess.names)}
+
+
+# ------------------------------------------------------------------------ activation cache
+class ActivationCache:
+    """Any tensor of the graph for all images of a shard, resident in HBM
+    (forward_net.py:23-189 keeps NumPy lists on the host and builds one ORT session per
+    node). `cache[name]` -> float32 CUDA tensor [n, ...]; initializers return the array."""
+
+    def __init__(self, graph, args, st=None, ed=None, engine=None):
+        self.graph = graph
+        self.args = args
+        self.st = 0 if st is None else st
+        self.ed = args.data_num if st is None else ed
+        self.device = _device_of(args)
+        self.engine = engine or Engine(graph, self.device, _unit_test_cpu=self.device.type != "cuda")
+        self.source = as_input_source(args.input_dir)
+        self.batch_size = int(getattr(args, "calib_bs", 0) or 64)
+        self.activation_cache = {}
+        self.in_shapes = {n: _per_image_shape(graph, n) for n in graph.network_inputs}
+
+    def update_graph(self, graph):
+        """New weights, same topology (forward_net.py:182-189)."""
+        self.graph = graph
+        self.engine.g = graph
+        self.engine.refresh_initializers()
+
+    def reset(self):
+        self.activation_cache.clear()
+
+    def __getitem__(self, name):
+        return self.get([name])[name]
+
+    def get(self, names, keep=True):
+        names = list(names)
+        out = {}
+        missing = []
+        for n in names:
+            if n in self.graph.initializer:
+                out[n] = self.graph.get_initializer(n)
+            elif n in self.activation_cache:
+                out[n] = self.activation_cache[n]
+            else:
+                missing.append(n)
+        if missing:
+            parts = {n: [] for n in missing}
+            for b0 in range(self.st, self.ed, self.batch_size):
+                b1 = min(b0 + self.batch_size, self.ed)
+                feeds = {nm: self.source.fetch(nm, b0, b1, shp).to(self.device, non_blocking=True)
+                         for nm, shp in self.in_shapes.items()}
+                cache = {k: v[b0 - self.st:b1 - self.st] for k, v in self.activation_cache.items()}
+                res = self.engine.run(feeds, want=missing, cache=cache)
+                for n in missing:
+                    parts[n].append(res[n])
+            for n in missing:
+                out[n] = torch.cat(parts[n], 0) if len(parts[n]) > 1 else parts[n][0]
+                if keep:
+                    self.activation_cache[n] = out[n]
+        return out
+
+    def drop(self, names):
+        for n in names:
+            self.activation_cache.pop(n, None)
+
+
+def forward_get_tensor(graph, net, index, args, engine=None):
+    """All non-Q/DQ node outputs of one image (forward_net.py:467-485). `net` is kept for
+    signature compatibility."""
+    dev = _device_of(args)
+    engine = engine or Engine(graph, dev, _unit_test_cpu=dev.type != "cuda")
+    src = as_input_source(args.input_dir)
+    feeds = {n: src.fetch(n, index, index + 1, _per_image_shape(graph, n)).to(dev)
+             for n in graph.network_inputs}
+    return engine.run(feeds, want="all")

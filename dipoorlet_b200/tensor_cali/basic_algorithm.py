@@ -1,0 +1,92 @@
+"""The activation calibrators behind `tensor_cali_dispatcher` — same registry keys,
+signatures and return values as dipoorlet/tensor_cali/basic_algorithm.py:8-91 — computed
+from device-resident statistics (forward_net.CalibrationSession) instead of per-image
+NumPy lists. With several ranks the statistics (not the clip values) are combined, see
+dist_helper.py."""
+import numpy as np
+
+from .. import dist_helper
+from .. import forward_net as fwd
+from ..platform_settings import LAYER_HAS_WEIGHT
+from ..utils import dispatch_functool, logger
+
+
+@dispatch_functool
+def tensor_cali_dispatcher(*args, **kwargs):
+    logger.info("Calibration Algorithm Not Found!")
+
+
+def _global_images(sess, t):
+    return dist_helper.allgather_images(t).cpu().numpy()
+
+
+@tensor_cali_dispatcher.register('minmax')
+def find_clip_val_minmax(onnx_graph, args, **kwargs):
+    """[min over images, max over images] per blob (basic_algorithm.py:13-22)."""
+    fwd.forward_get_minmax(onnx_graph, args)
+    sess = fwd._session(onnx_graph, args)
+    dist_helper.allreduce_minmax(sess.blob_min, sess.blob_max)
+    lo, hi = sess.blob_min.cpu().numpy(), sess.blob_max.cpu().numpy()
+    return {name: [lo[i], hi[i]] for i, name in enumerate(sess.names)}
+
+
+@tensor_cali_dispatcher.register('hist')
+def find_clip_val_hist(onnx_graph, args, store_stats=None, **kwargs):
+    """Percentile of the |x| histogram (basic_algorithm.py:25-54): pass 1 range, pass 2
+    histogram with the global range, K3 search on the device."""
+    sess = fwd._session(onnx_graph, args, fresh=True)
+    bins = int(args.bins)
+    if store_stats:
+        import torch
+        mm, hist = store_stats['minmax'], store_stats['hist']
+        sess.blob_min.copy_(torch.tensor([np.min(mm[n]['min']) for n in sess.names], dtype=torch.float32))
+        sess.blob_max.copy_(torch.tensor([np.max(mm[n]['max']) for n in sess.names], dtype=torch.float32))
+        from .. import kernels as K
+        sess.data_max = torch.empty(sess.n_stats, dtype=torch.float32, device=sess.device)
+        K.absmax(sess.blob_min, sess.blob_max, sess.data_max)
+        sess.counts = torch.from_numpy(np.stack([np.asarray(hist[n], dtype=np.int64) for n in sess.names])
+                                       ).to(sess.device).contiguous()
+    else:
+        sess.run_minmax()
+        sess.run_hist(bins)
+    clip, sel = sess.percentile_clip(bins, args.threshold)
+    clip = clip.cpu().numpy()
+    return {name: [clip[i, 0], clip[i, 1]] for i, name in enumerate(sess.names)}
+
+
+@tensor_cali_dispatcher.register('mse')
+def find_clip_val_octav(onnx_graph, args, **kwargs):
+    """OCTAV (basic_algorithm.py:57-69): per-image fixed point on the device (K4), then the
+    reference's own float32 mean over images on the host (123 x N values)."""
+    fwd.forward_net_octav(onnx_graph, args)
+    sess = fwd._session(onnx_graph, args)
+    s = _global_images(sess, sess.seg_s)
+    mx = _global_images(sess, sess.seg_max)
+    mn = _global_images(sess, sess.seg_min)
+    clip_val = {}
+    for i, name in enumerate(sess.names):
+        data_max, data_min = mx[i].max(), mn[i].min()
+        m = s[i].mean()
+        clip_val[name] = [max(data_min, -m), min(data_max, m)]
+    return clip_val
+
+
+def find_clip_val_minmax_weight(onnx_graph, args):
+    """Per-output-channel min / max of every weight-like initializer (host side, a few
+    ms; basic_algorithm.py:72-91)."""
+    tensors, transposed = {}, set()
+    for node in onnx_graph.graph.node:
+        if node.op_type in LAYER_HAS_WEIGHT:
+            for name in node.input[1:]:
+                tensors[name] = onnx_graph.get_initializer(name)
+            if node.op_type == 'ConvTranspose':
+                transposed.add(node.input[1])
+    out = {}
+    for name, t in tensors.items():
+        if t.ndim < 1:
+            continue
+        if name in transposed:
+            t = t.transpose([1, 0, 2, 3])
+        flat = t.reshape((t.shape[0], -1))
+        out[name] = [flat.min(-1), flat.max(-1)]
+    return out

@@ -67,7 +67,7 @@ def test_segstats_matches_oracle(dpl_built):
         assert bmin[i].item() == clip[name][0] and bmax[i].item() == clip[name][1]
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 7])
 @pytest.mark.parametrize("bins", [2048, 128, 1000])
 def test_hist_bit_exact(dpl_built, variant, bins):
     import torch
@@ -117,7 +117,7 @@ def test_hist_edge_values_bit_exact(dpl_built):
         smin, smax, ssum, snnz, bmin, bmax = _run_segstats(batch, torch, K)
         dmt = torch.empty(1, dtype=torch.float32, device=batch.device)
         K.absmax(bmin, bmax, dmt)
-        for variant in (1, 2, 3):
+        for variant in (1, 2, 3, 4, 5, 7):
             counts = torch.zeros((1, bins), dtype=torch.int64, device=batch.device)
             K.hist_abs(batch, dmt, counts, bins, variant=variant)
             want = np.histogram(np.abs(blobs["e"][0]), bins, (0, dm))[0]

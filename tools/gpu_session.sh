@@ -1,0 +1,24 @@
+#!/bin/bash
+# One GPU lease, many measurements (each gpurun call is charged a ~10 min minimum).
+# Every step has its own timeout and writes straight into gpurun_out/ so that a hang in
+# one step loses nothing else.  Usage: tools/gpu_session.sh [steps...]  (default: all)
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+STEPS="${@:-tests kbench bench ref launches ncu smoke}"
+for s in $STEPS; do
+  echo "=== $s $(date +%T)" | tee -a gpurun_out/session.log
+  case $s in
+    tests)   timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log ;;
+    kbench)  timeout 300 python tools/kbench.py --batch 32 > gpurun_out/kbench.log 2>&1; cat gpurun_out/kbench.log | tail -40 ;;
+    bench)   timeout 600 python bench.py --steps 3 --warmup 3 --hist-variant ${HIST_VARIANT:-4} > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err ;;
+    ref)     timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 1500 gpurun_out/bench_ref.json ;;
+    launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv \
+                 --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --images 64 --no-cpu-baseline \
+                 > gpurun_out/launches_run.log 2>&1; tail -3 gpurun_out/launches_run.log ;;
+    ncu)     timeout 600 ncu --set full --clock-control none --import-source on \
+                 -k regex:'hist_lc|hist_lanecol|segstats_tiles|octav' -c 8 -f -o gpurun_out/prof_r1 \
+                 python tools/kbench.py --batch 16 --quick > gpurun_out/ncu_run.log 2>&1; tail -3 gpurun_out/ncu_run.log ;;
+    smoke)   timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3 ;;
+  esac
+done
+echo "=== done $(date +%T)" | tee -a gpurun_out/session.log

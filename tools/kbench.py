@@ -36,6 +36,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--out", default="gpurun_out/kbench.json")
+    ap.add_argument("--quick", action="store_true", help="one data mode, one launch per kernel (for ncu)")
     args = ap.parse_args()
     peak = 6483.3
     try:
@@ -45,7 +46,10 @@ def main():
     dev = torch.device("cuda:0")
     shapes = resnet50_blob_shapes()
     res = {"batch": args.batch, "peak_gbs": peak, "rows": []}
-    for mode in ("mixed", "dense", "relu"):
+    if args.quick:
+        global timed
+        timed = lambda fn, iters=1, warm=0: (fn(), torch.cuda.synchronize(), (1.0, 1.0))[2]  # noqa: E731
+    for mode in (("mixed",) if args.quick else ("mixed", "dense", "relu")):
         g = torch.Generator(device=dev).manual_seed(0)
         tensors = []
         for i, shp in enumerate(shapes):
@@ -68,7 +72,7 @@ def main():
                             "gbs": nbytes / med / 1e6, "frac": nbytes / med / 1e6 / peak})
         dm = torch.empty(batch.n_blobs, device=dev)
         K.absmax(bmin, bmax, dm)
-        for variant in (1, 3, 2):
+        for variant in ((4, 7) if args.quick else (1, 4, 5, 7, 3, 2)):
             counts = torch.zeros((batch.n_blobs, 2048), dtype=torch.int64, device=dev)
             med, best = timed(lambda: K.hist_abs(batch, dm, counts, 2048, variant=variant))
             res["rows"].append({"kernel": f"K2 hist v{variant}", "mode": mode, "ms": med,
