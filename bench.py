@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--hist-variant", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--resident", type=int, default=None, choices=[0, 1],
+                    help="keep pass-1 blobs resident in HBM for pass 2 (default: auto)")
     return ap.parse_args()
 
 
@@ -197,7 +199,8 @@ def run_ours(args):
     def mk_args(source):
         return make_args(input_dir=source, data_num=n_img * world, deploy="trt", act_quant="hist",
                          bins=BINS, threshold=THRESHOLD, output_dir="/tmp/dpl_bench",
-                         calib_bs=args.batch, rank=rank, local_rank=local_rank, world_size=world)
+                         calib_bs=args.batch, rank=rank, local_rank=local_rank, world_size=world,
+                         resident=args.resident)
 
     hist_events = []
 
@@ -257,19 +260,23 @@ def run_ours(args):
     # ---- e2e: plugin API from pinned host buffers -----------------------------------------
     d2h = {"n": 0}
 
+    resident_used = {"v": False}
+
     def e2e_job():
         a = mk_args(host)
         a.act_quant = "hist"
         fwd._SESSIONS.clear()
         act, weight = tensor_calibration(graph, a)   # host dict of np.float32 clip values
         d2h["n"] = 8 * len(act)
+        resident_used["v"] = bool(fwd._session(graph, a).keep_resident)
         return act
 
     for _ in range(max(1, min(args.warmup, 3))):
         e2e_job()
     ms_e2e = timed(e2e_job, args.steps)
     e2e_value = n_img * world * args.steps / (ms_e2e / 1e3)
-    h2d_per_step = 2 * images.nbytes * world  # both passes re-send the images
+    passes = 1 if resident_used["v"] else 2   # recompute mode re-sends the images for pass 2
+    h2d_per_step = passes * images.nbytes * world
 
     if rank != 0:
         return
@@ -281,7 +288,8 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "images_per_gpu": n_img, "forward_batch": args.batch,
                    "l2": "inputs larger than L2: every timed kernel streams a %.1f GB batch of blobs "
                          "(126 MB L2)" % (4 * elems_per_img * args.batch / 1e9),
-                   "forward": "torch/cuDNN fp32 (TF32 off) stand-in producer; statistics = libdpl_b200.so"},
+                   "forward": "torch/cuDNN fp32 (TF32 off) stand-in producer; statistics = libdpl_b200.so",
+                   "resident_blobs": bool(resident_used["v"])},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_per_step,
                 "d2h_bytes_per_step": d2h["n"], "ms_per_step": ms_e2e / args.steps},

@@ -40,6 +40,8 @@ def build_parser():
     p.add_argument("--model_type", help="Transformer model type", choices=["unet"], default=None)
     p.add_argument("--quant_format", default="QDQ", type=str, choices=["QOP", "QDQ"])
     p.add_argument("--calib_bs", help="images per GPU forward batch (0 = auto)", type=int, default=0)
+    p.add_argument("--resident", help="keep pass-1 blobs in HBM for the histogram pass (default: auto, "
+                   "when they fit)", type=int, default=None, choices=[0, 1])
     return p
 
 

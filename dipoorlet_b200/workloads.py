@@ -97,16 +97,58 @@ class _Builder:
         return self.ol.Model(self.g, ir_version=7, opsets={"": 13})
 
 
-def build_resnet50(seed=0, blocks=None, width=64, num_classes=1000, image=224):
+class _MiniResNet:
+    """Bottleneck ResNet with free stage widths (torchvision.models.ResNet hard-codes 64..512);
+    same attribute names, same initialisation, used for small test fixtures."""
+
+    def __init__(self, blocks, planes, stem, num_classes):
+        import torch.nn as nn
+        from torchvision.models.resnet import Bottleneck
+        self.conv1 = nn.Conv2d(3, stem, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(stem)
+        inplanes = stem
+        self.layers = []
+        for i, (p, n) in enumerate(zip(planes, blocks)):
+            stage = []
+            for j in range(n):
+                stride = 2 if (j == 0 and i > 0) else 1
+                down = None
+                if stride != 1 or inplanes != p * 4:
+                    down = nn.Sequential(nn.Conv2d(inplanes, p * 4, 1, stride, bias=False),
+                                         nn.BatchNorm2d(p * 4))
+                stage.append(Bottleneck(inplanes, p, stride, down))
+                inplanes = p * 4
+            self.layers.append(stage)
+        self.fc = nn.Linear(inplanes, num_classes)
+        self._mods = [self.conv1, self.bn1, self.fc] + [b for st in self.layers for b in st]
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+    def modules(self):
+        for top in self._mods:
+            yield from top.modules()
+
+    def eval(self):
+        for m in self._mods:
+            m.eval()
+
+
+def build_resnet50(seed=0, blocks=None, width=64, num_classes=1000, image=224, planes=None, stem=64):
     """BN-folded torchvision ResNet-50 (53 Conv, 49 Relu, 16 Add, MaxPool,
     GlobalAveragePool, Flatten, Gemm = 122 nodes, 123 blobs) with seeded random weights.
-    `blocks` / `width` shrink it for tests (e.g. blocks=[1,1,1,1], width=16)."""
+    `blocks` / `width` / `planes` / `stem` shrink it for tests and fixtures."""
     import torch
     import torchvision
     gen = torch.Generator().manual_seed(seed)
     torch.manual_seed(seed)
-    net = torchvision.models.ResNet(torchvision.models.resnet.Bottleneck, blocks or [3, 4, 6, 3],
-                                    num_classes=num_classes, width_per_group=width)
+    if planes is not None:
+        net = _MiniResNet(blocks or [1, 1, 1, 1], planes, stem, num_classes)
+        stages = net.layers
+    else:
+        net = torchvision.models.ResNet(torchvision.models.resnet.Bottleneck, blocks or [3, 4, 6, 3],
+                                        num_classes=num_classes, width_per_group=width)
+        stages = (net.layer1, net.layer2, net.layer3, net.layer4)
     _randomise_bn(net, gen)
     net.eval()
     b = _Builder("resnet50", (3, image, image))
@@ -114,7 +156,7 @@ def build_resnet50(seed=0, blocks=None, width=64, num_classes=1000, image=224):
     x = b.add("Relu", [x])
     x = b.add("MaxPool", [x], {"kernel_shape": [3, 3], "pads": [1, 1, 1, 1], "strides": [2, 2],
                                "ceil_mode": 0})
-    for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
+    for layer in stages:
         for blk in layer:
             idt = x
             y = b.add("Relu", [b.conv(x, blk.conv1, blk.bn1)])

@@ -1,0 +1,122 @@
+"""The oracle and the product's host logic against fixtures produced by the REFERENCE
+ITSELF (tests/golden/*, written by oracle/gen_golden.py which runs /root/reference's
+modules under stand-ins for onnx / onnxruntime). This is what pins the oracle."""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MODELS = ["tiny_r50", "tiny_mbv2"]
+
+
+def _load(mname):
+    from dipoorlet_b200 import onnx_lite as ol
+    d = os.path.join(GOLD, mname)
+    model = ol.load(os.path.join(d, "model.onnx"))
+    images = np.load(os.path.join(d, "images.npy"))
+    calib = json.load(open(os.path.join(d, "calibration.json")))
+    return d, model, images, calib
+
+
+@pytest.mark.parametrize("mname", MODELS)
+@pytest.mark.parametrize("algo", ["minmax", "hist", "mse"])
+def test_oracle_calibration_equals_reference(mname, algo):
+    """oracle.pipeline (forward + statistics + clip search) == reference tensor_calibration,
+    value for value, and the files written from it are byte-identical."""
+    from oracle import pipeline as P
+    from oracle import stats as O
+    d, model, images, calib = _load(mname)
+    got = P.calibrate(model, images, algo)
+    want = calib[algo]["act"]
+    assert list(got) == list(want)
+    for k in want:
+        assert float(got[k][0]) == want[k][0] and float(got[k][1]) == want[k][1], (k, got[k], want[k])
+    # act_clip_val.json as save_clip_val writes it, and trt_clip_val.json
+    text = json.dumps({k: [np.asarray(v[0]).tolist(), np.asarray(v[1]).tolist()] for k, v in got.items()}, indent=4)
+    assert text == calib[algo]["act_clip_val_json"]
+    trt = json.dumps({"blob_range": {k: float(v) for k, v in O.trt_blob_range(got).items()}}, indent=4)
+    assert trt == calib[algo]["trt_clip_val_json"]
+
+
+@pytest.mark.parametrize("mname", MODELS)
+def test_product_files_byte_identical(mname, tmp_path):
+    """save_clip_val / load_clip_val / to_deploy('trt') of the product reproduce the
+    reference's files byte for byte when fed the reference's clip values."""
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.deploy import to_deploy
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.tensor_cali import find_clip_val_minmax_weight
+    from dipoorlet_b200.utils import load_clip_val, save_clip_val
+    d, model, images, calib = _load(mname)
+    graph = ONNXGraph(model, str(tmp_path), "trt")
+    args = make_args(input_dir="unused", data_num=8, deploy="trt", output_dir=str(tmp_path))
+    weight = find_clip_val_minmax_weight(graph, args)
+    gold_w = np.load(os.path.join(d, "weight_clip.npz"))
+    assert sorted(f"{k}|{i}" for k in weight for i in (0, 1)) == sorted(gold_w.files)
+    for k in weight:
+        assert np.array_equal(weight[k][0], gold_w[f"{k}|0"]) and np.array_equal(weight[k][1], gold_w[f"{k}|1"])
+    for algo in ("minmax", "hist", "mse"):
+        act = {k: [np.float32(v[0]), np.float32(v[1])] for k, v in calib[algo]["act"].items()}
+        save_clip_val(act, copy.deepcopy(weight), args)
+        assert open(tmp_path / "act_clip_val.json").read() == calib[algo]["act_clip_val_json"]
+        act2, w2 = load_clip_val(args)
+        to_deploy(graph, act2, w2, args)
+        assert open(tmp_path / "trt_clip_val.json").read() == calib[algo]["trt_clip_val_json"]
+
+
+@pytest.mark.parametrize("mname", MODELS)
+def test_quant_graph_equals_reference(mname, tmp_path):
+    """Which tensors get Q/DQ pairs (merged ReLU, TensorRT add-merge, per-channel weights),
+    node order, names, rewiring and the scale / zero-point initializers."""
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.quantize import quant_graph
+    d, model, images, calib = _load(mname)
+    graph = ONNXGraph(model, str(tmp_path), "trt")
+    args = make_args(input_dir="unused", data_num=8, deploy="trt", output_dir=str(tmp_path))
+    gold_w = np.load(os.path.join(d, "weight_clip.npz"))
+    clip = {k: [np.float64(v[0]), np.float64(v[1])] for k, v in calib["minmax"]["act"].items()}
+    for key in gold_w.files:
+        name, i = key.rsplit("|", 1)
+        clip.setdefault(name, [None, None])[int(i)] = gold_w[key]
+    gq, qlist = quant_graph(graph, copy.deepcopy(clip), args)
+    want = json.load(open(os.path.join(d, "quant_graph.json")))
+    assert [n.name for n in qlist] == want["quant_node_list"]
+    got_nodes = [[n.op_type, n.name, list(n.input), list(n.output),
+                  {k: v for k, v in n.attrs.items() if k == "axis"}] for n in gq.graph.node]
+    assert got_nodes == want["nodes"]
+    qp = np.load(os.path.join(d, "quant_params.npz"))
+    inits = gq.model.graph.initializers
+    for name in qp.files:
+        assert name in inits, name
+        assert inits[name].dtype == qp[name].dtype and np.array_equal(inits[name].reshape(-1), qp[name].reshape(-1)), name
+
+
+@pytest.mark.parametrize("mname", MODELS)
+def test_oracle_qdq_forward_equals_reference(mname, tmp_path):
+    """fp and Q/DQ graph activations (ActivationCache of the reference) == the oracle forward
+    on the product's Q/DQ graph: pins the fake-quant semantics end to end."""
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.quantize import quant_graph
+    from oracle import forward as OF
+    d, model, images, calib = _load(mname)
+    graph = ONNXGraph(model, str(tmp_path), "trt")
+    args = make_args(input_dir="unused", data_num=8, deploy="trt", output_dir=str(tmp_path))
+    gold_w = np.load(os.path.join(d, "weight_clip.npz"))
+    clip = {k: [np.float64(v[0]), np.float64(v[1])] for k, v in calib["minmax"]["act"].items()}
+    for key in gold_w.files:
+        name, i = key.rsplit("|", 1)
+        clip.setdefault(name, [None, None])[int(i)] = gold_w[key]
+    gq, _ = quant_graph(graph, copy.deepcopy(clip), args)
+    gold = np.load(os.path.join(d, "qforward.npz"))
+    n = images.shape[0]
+    fp = OF.blobs_for_images(model, {"input": images}, n)
+    q = OF.blobs_for_images(gq.model, {"input": images}, n)
+    for key in gold.files:
+        kind, t = key.split("|", 1)
+        src = fp[t] if kind == "fp" else q[t if t in q else t + "_dq"]
+        assert np.array_equal(np.stack(src), gold[key]), key

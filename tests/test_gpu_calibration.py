@@ -28,9 +28,14 @@ def setup(dpl_built, tmp_path_factory):
     images = W.synthetic_images(N, (3, IMG, IMG), seed=3)
     args = make_args(input_dir=ArrayInput({"input": images[:, 0]}), data_num=N, deploy="trt",
                      output_dir=out, calib_bs=5)
+    # "the same blobs": the session runs batches of calib_bs images, and cuDNN may pick a
+    # different (differently rounding) algorithm per batch size, so reproduce its batching
     eng = Engine(graph, torch.device("cuda", 0))
-    blobs_dev = eng.run({"input": torch.from_numpy(images[:, 0]).cuda()}, want="all")
-    blobs = {k: [v[i].cpu().numpy()[None] for i in range(N)] for k, v in blobs_dev.items()}
+    blobs = {}
+    for b0 in range(0, N, args.calib_bs):
+        part = eng.run({"input": torch.from_numpy(images[b0:b0 + args.calib_bs, 0]).cuda()}, want="all")
+        for k, v in part.items():
+            blobs.setdefault(k, []).extend(v[i].cpu().numpy()[None] for i in range(v.shape[0]))
     return dict(graph=graph, args=args, images=images, blobs=blobs, model=model, out=out)
 
 
