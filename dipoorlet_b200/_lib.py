@@ -58,6 +58,13 @@ SIGNATURES = {
     "dpl_adaround_step_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_u64, _c_flt, _c_flt, _c_flt,
                                        _c_flt, _c_flt, _c_flt, _c_flt, _c_flt, _c_int, _c_flt,
                                        _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "dpl_recon_act_f32": (_c_int, [_c_vp, _c_vp, _c_u64, _c_int, _c_int, _c_flt, _c_flt, _c_flt, _c_flt,
+                                   _c_u64, _c_vp]),
+    "dpl_recon_act_bwd_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_u64, _c_int, _c_int, _c_flt, _c_flt,
+                                       _c_flt, _c_flt, _c_u64, _c_vp]),
+    "dpl_recon_loss_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_u64, _c_int, _c_int, _c_flt, _c_flt, _c_flt,
+                                    _c_flt, _c_u64, _c_flt, _c_vp, _c_vp]),
+    "dpl_mix_drop_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_u64, _c_flt, _c_u64, _c_vp]),
 }
 
 

@@ -104,13 +104,20 @@ class Engine:
         names = self.blob_names() if want_all else [w for w in want]
         return OrderedDict((n, env[n]) for n in names if n in env)
 
-    def _needed_nodes(self, wanted, env):
+    def inputs_required(self, want, have):
+        """Network inputs that must be fed to compute `want` when the tensors in `have` are
+        already available (lets ActivationCache skip the host->device copy of the images)."""
+        need = self._needed_nodes(set(want), {k: None for k in have}, strict=False)
+        used = {t for i in need for t in self.nodes[i].input}
+        return [n for n in self.g.network_inputs if (n in used or n in want) and n not in have]
+
+    def _needed_nodes(self, wanted, env, strict=True):
         need, stack = set(), [w for w in wanted if w not in env]
         while stack:
             t = stack.pop()
             prod = self.g.output_map.get(t)
             if prod is None:
-                if t not in self.params and t not in env and t != "":
+                if strict and t not in self.params and t not in env and t != "":
                     raise KeyError(f"tensor {t!r} has no producer and was not fed")
                 continue
             idx = self.g.name_idx_map[prod.name]

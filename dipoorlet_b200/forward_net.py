@@ -277,14 +277,37 @@ class ActivationCache:
         self.engine = engine or Engine(graph, self.device, _unit_test_cpu=self.device.type != "cuda")
         self.source = as_input_source(args.input_dir)
         self.batch_size = int(getattr(args, "calib_bs", 0) or 64)
+        self.max_cached = 6        # whole-shard tensors kept in HBM (least recently used evicted)
         self.activation_cache = {}
         self.in_shapes = {n: _per_image_shape(graph, n) for n in graph.network_inputs}
 
     def update_graph(self, graph):
-        """New weights, same topology (forward_net.py:182-189)."""
+        """New weights, same topology (forward_net.py:182-189): every cached activation is
+        dropped. Prefer `update_initializers`, which keeps what is still valid."""
         self.graph = graph
         self.engine.g = graph
         self.engine.refresh_initializers()
+        self.activation_cache.clear()
+
+    def update_initializers(self, names, node):
+        """The initializers `names` of `node` changed (a rounded weight, a corrected bias):
+        re-upload them and drop exactly the cached activations downstream of `node` — what
+        the reference's incremental `prev_act_cache` bookkeeping achieves (adaround.py:41-54)."""
+        self.engine.refresh_initializers(names)
+        dead = self._downstream(node)
+        for t in [t for t in self.activation_cache if t in dead]:
+            del self.activation_cache[t]
+
+    def _downstream(self, node):
+        seen, stack = set(), list(node.output)
+        while stack:
+            t = stack.pop()
+            if t in seen:
+                continue
+            seen.add(t)
+            for consumer in self.graph.input_map.get(t, []):
+                stack.extend(consumer.output)
+        return seen
 
     def reset(self):
         self.activation_cache.clear()
@@ -301,15 +324,17 @@ class ActivationCache:
                 out[n] = self.graph.get_initializer(n)
             elif n in self.activation_cache:
                 out[n] = self.activation_cache[n]
+                self.activation_cache[n] = self.activation_cache.pop(n)   # most recently used
             else:
                 missing.append(n)
         if missing:
             parts = {n: [] for n in missing}
+            fed = self.engine.inputs_required(missing, self.activation_cache.keys())
             for b0 in range(self.st, self.ed, self.batch_size):
                 b1 = min(b0 + self.batch_size, self.ed)
-                feeds = {nm: self.source.fetch(nm, b0, b1, shp).to(self.device, non_blocking=True)
-                         for nm, shp in self.in_shapes.items()}
                 cache = {k: v[b0 - self.st:b1 - self.st] for k, v in self.activation_cache.items()}
+                feeds = {nm: self.source.fetch(nm, b0, b1, self.in_shapes[nm]).to(self.device, non_blocking=True)
+                         for nm in fed}
                 res = self.engine.run(feeds, want=missing, cache=cache)
                 for n in missing:
                     parts[n].append(res[n])
@@ -317,6 +342,8 @@ class ActivationCache:
                 out[n] = torch.cat(parts[n], 0) if len(parts[n]) > 1 else parts[n][0]
                 if keep:
                     self.activation_cache[n] = out[n]
+            while len(self.activation_cache) > self.max_cached:   # least recently used first
+                self.activation_cache.pop(next(iter(self.activation_cache)))
         return out
 
     def drop(self, names):

@@ -236,3 +236,46 @@ def adaround_step(grad_w, wfloor, scale, qmin, qmax, beta, alpha, m, v, step, re
                                       v.data_ptr(), _lib._ptr(reg_out), _stream()),
           "dpl_adaround_step_f32")
     _count()
+
+
+def recon_act(o, relu, quant=None, prob=1.0, seed=0, out=None):
+    """K6 epilogue forward. quant: None or (scale, qmin, qmax) per-tensor."""
+    y = torch.empty_like(o) if out is None else out
+    s, lo, hi = quant if quant else (1.0, 0.0, 0.0)
+    check(lib().dpl_recon_act_f32(o.data_ptr(), y.data_ptr(), o.numel(), int(bool(relu)),
+                                  int(quant is not None), float(s), float(lo), float(hi), float(prob),
+                                  int(seed) & (2 ** 64 - 1), _stream()), "dpl_recon_act_f32")
+    _count()
+    return y
+
+
+def recon_act_bwd(o, gy, relu, quant=None, prob=1.0, seed=0, out=None):
+    go = torch.empty_like(o) if out is None else out
+    s, lo, hi = quant if quant else (1.0, 0.0, 0.0)
+    check(lib().dpl_recon_act_bwd_f32(o.data_ptr(), gy.data_ptr(), go.data_ptr(), o.numel(),
+                                      int(bool(relu)), int(quant is not None), float(s), float(lo),
+                                      float(hi), float(prob), int(seed) & (2 ** 64 - 1), _stream()),
+          "dpl_recon_act_bwd_f32")
+    _count()
+    return go
+
+
+def recon_loss(o, tgt, inv_count, loss_acc, relu, quant=None, prob=1.0, seed=0, out=None):
+    """Accumulates the L2 loss into loss_acc (float64[1]) and returns dL/do."""
+    go = torch.empty_like(o) if out is None else out
+    s, lo, hi = quant if quant else (1.0, 0.0, 0.0)
+    check(lib().dpl_recon_loss_f32(o.data_ptr(), tgt.data_ptr(), go.data_ptr(), o.numel(),
+                                   int(bool(relu)), int(quant is not None), float(s), float(lo),
+                                   float(hi), float(prob), int(seed) & (2 ** 64 - 1),
+                                   float(inv_count), _lib._ptr(loss_acc), _stream()),
+          "dpl_recon_loss_f32")
+    _count()
+    return go
+
+
+def mix_drop(a, b, prob, seed, out=None):
+    y = torch.empty_like(a) if out is None else out
+    check(lib().dpl_mix_drop_f32(a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), float(prob),
+                                 int(seed) & (2 ** 64 - 1), _stream()), "dpl_mix_drop_f32")
+    _count()
+    return y

@@ -162,6 +162,23 @@ int dpl_adaround_step_f32(const float* d_grad_w, const float* d_wfloor, const fl
                           float grad_scale, float* d_alpha, float* d_m, float* d_v,
                           double* d_reg, void* stream);
 
+/* K6 epilogues — layer activation of the reconstruction loop: y = [drop-]fakequant(relu(o))
+ * (AdaQLayer.forward tail, weight_transform/ada_quant_layer.py:245-251; quant_acti :28-36),
+ * its backward (round() has zero gradient: only non-quantised elements pass), the fused
+ * L2 loss + dL/do of the block output (L2_norm :113-114: sum over channels, mean over the
+ * rest => inv_count = channels / numel), and the QDrop block input
+ * where(u < prob, q_in, fp_in) (brecq.py:169-170). Masks are regenerated from (seed, index). */
+int dpl_recon_act_f32(const float* d_o, float* d_y, uint64_t n, int relu, int quant, float scale,
+                      float qmin, float qmax, float prob, uint64_t seed, void* stream);
+int dpl_recon_act_bwd_f32(const float* d_o, const float* d_gy, float* d_go, uint64_t n, int relu,
+                          int quant, float scale, float qmin, float qmax, float prob,
+                          uint64_t seed, void* stream);
+int dpl_recon_loss_f32(const float* d_o, const float* d_tgt, float* d_go, uint64_t n, int relu,
+                       int quant, float scale, float qmin, float qmax, float prob, uint64_t seed,
+                       float inv_count, double* d_loss, void* stream);
+int dpl_mix_drop_f32(const float* d_a, const float* d_b, float* d_y, uint64_t n, float prob,
+                     uint64_t seed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
