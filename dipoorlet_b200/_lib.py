@@ -64,6 +64,10 @@ SIGNATURES = {
                                        _c_flt, _c_flt, _c_u64, _c_vp]),
     "dpl_recon_loss_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_u64, _c_int, _c_int, _c_flt, _c_flt, _c_flt,
                                     _c_flt, _c_u64, _c_flt, _c_vp, _c_vp]),
+    "dpl_gemm_tf32": (_c_int, [_c_vp, _c_int, ctypes.c_longlong, ctypes.c_longlong, _c_vp, _c_int,
+                               ctypes.c_longlong, ctypes.c_longlong, _c_vp, ctypes.c_longlong,
+                               ctypes.c_longlong, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp,
+                               _c_int, _c_int, _c_vp, _c_vp]),
     "dpl_mix_drop_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_u64, _c_flt, _c_u64, _c_vp]),
 }
 

@@ -145,8 +145,14 @@ constexpr float kZeta = 1.1f, kGamma = -0.1f;
 
 __device__ __forceinline__ float sigmoidf_(float a) { return __fdiv_rn(1.0f, 1.0f + expf(-a)); }
 // h(alpha) = clamp((zeta - gamma) * sigmoid(alpha) + gamma, 0, 1)
+// torch evaluates the product and the sum separately (no FMA); at the clamp boundary
+// (rest == 0, i.e. the largest weight of every channel, w/s = +-127) a fused evaluation can
+// land on the other side of 0 and flip the clamp's gradient mask.
+__device__ __forceinline__ float rect_sigmoid_raw(float sg) {
+  return __fadd_rn(__fmul_rn(kZeta - kGamma, sg), kGamma);
+}
 __device__ __forceinline__ float rect_sigmoid(float a) {
-  return fminf(fmaxf(fmaf(kZeta - kGamma, sigmoidf_(a), kGamma), 0.f), 1.f);
+  return fminf(fmaxf(rect_sigmoid_raw(sigmoidf_(a)), 0.f), 1.f);
 }
 
 __global__ void __launch_bounds__(256)
@@ -193,7 +199,7 @@ adaround_step_kernel(const float* __restrict__ grad_w, const float* __restrict__
     const float s = scale[n_channels == 1 ? 0 : (i / inner) % (uint64_t)n_channels];
     const float a = alpha[i];
     const float sg = sigmoidf_(a);
-    const float hraw = fmaf(kZeta - kGamma, sg, kGamma);
+    const float hraw = rect_sigmoid_raw(sg);
     const float h = fminf(fmaxf(hraw, 0.f), 1.f);
     // clamp(0,1) passes the gradient on the closed interval (torch.clamp backward)
     const float dh = (hraw >= 0.f && hraw <= 1.f) ? (kZeta - kGamma) * sg * (1.f - sg) : 0.f;

@@ -12,6 +12,7 @@ library call playing the role onnxruntime's CUDA EP plays in the reference. The 
 fake-quant and rounding kernels — the hot path this repo is about — are libdpl_b200.so.
 QuantizeLinear + DequantizeLinear pairs are executed as ONE fused K5 launch.
 """
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -70,6 +71,8 @@ class Engine:
         `cache` (dict) is consulted before computing a tensor and is not modified."""
         torch.backends.cudnn.allow_tf32 = self.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = self.allow_tf32
+        if os.environ.get("DPL_CUDNN_BENCHMARK"):   # let cuDNN time its fp32 algorithms per shape
+            torch.backends.cudnn.benchmark = os.environ["DPL_CUDNN_BENCHMARK"] == "1"
         env = dict(feeds)
         if cache:
             for k, v in cache.items():

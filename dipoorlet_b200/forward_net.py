@@ -277,8 +277,8 @@ class ActivationCache:
         self.engine = engine or Engine(graph, self.device, _unit_test_cpu=self.device.type != "cuda")
         self.source = as_input_source(args.input_dir)
         self.batch_size = int(getattr(args, "calib_bs", 0) or 64)
-        self.max_cached = 6        # whole-shard tensors kept in HBM (least recently used evicted)
         self.activation_cache = {}
+        self._pos_graph, self._pos_len = None, -1
         self.in_shapes = {n: _per_image_shape(graph, n) for n in graph.network_inputs}
 
     def update_graph(self, graph):
@@ -315,7 +315,28 @@ class ActivationCache:
     def __getitem__(self, name):
         return self.get([name])[name]
 
+    def _positions(self):
+        """producer index and last-consumer index of every tensor (network inputs: -1)."""
+        if self._pos_graph is not self.graph.model.graph.nodes or self._pos_len != len(self.graph.model.graph.nodes):
+            prod, last = {n: -1 for n in self.graph.network_inputs}, {}
+            for i, node in enumerate(self.graph.model.graph.nodes):
+                for o in node.output:
+                    prod[o] = i
+                for t in node.input:
+                    last[t] = i
+            for t in self.graph.network_outputs:
+                last[t] = len(self.graph.model.graph.nodes)
+            self._prod, self._last = prod, last
+            self._pos_graph, self._pos_len = self.graph.model.graph.nodes, len(self.graph.model.graph.nodes)
+        return self._prod, self._last
+
     def get(self, names, keep=True):
+        """Tensors for all images of the shard. Besides the requested tensors the cache keeps
+        the FRONTIER at the furthest requested node — every activation produced at or before
+        it and still consumed after it (for a ResNet: the main path and the identity branch) —
+        so that the next request further down the network resumes there instead of at the
+        images. Walking the layers in order therefore costs one forward in total, which is
+        what the reference's ref-counted NumPy cache achieves on the host (forward_net.py:81-136)."""
         names = list(names)
         out = {}
         missing = []
@@ -324,26 +345,35 @@ class ActivationCache:
                 out[n] = self.graph.get_initializer(n)
             elif n in self.activation_cache:
                 out[n] = self.activation_cache[n]
-                self.activation_cache[n] = self.activation_cache.pop(n)   # most recently used
             else:
                 missing.append(n)
         if missing:
-            parts = {n: [] for n in missing}
-            fed = self.engine.inputs_required(missing, self.activation_cache.keys())
+            prod, last = self._positions()
+            cut = max(prod.get(n, -1) for n in missing)
+            frontier = [t for t, pi in prod.items()
+                        if pi <= cut < last.get(t, -1) and t not in self.graph.initializer]
+            extra = [t for t in frontier if t not in self.activation_cache and t not in missing] if keep else []
+            want = missing + extra
+            parts = {n: [] for n in want}
+            fed = self.engine.inputs_required(want, self.activation_cache.keys())
             for b0 in range(self.st, self.ed, self.batch_size):
                 b1 = min(b0 + self.batch_size, self.ed)
                 cache = {k: v[b0 - self.st:b1 - self.st] for k, v in self.activation_cache.items()}
                 feeds = {nm: self.source.fetch(nm, b0, b1, self.in_shapes[nm]).to(self.device, non_blocking=True)
                          for nm in fed}
-                res = self.engine.run(feeds, want=missing, cache=cache)
-                for n in missing:
+                res = self.engine.run(feeds, want=want, cache=cache)
+                for n in want:
                     parts[n].append(res[n])
-            for n in missing:
-                out[n] = torch.cat(parts[n], 0) if len(parts[n]) > 1 else parts[n][0]
+            for n in want:
+                t = torch.cat(parts[n], 0) if len(parts[n]) > 1 else parts[n][0]
+                if n in missing:
+                    out[n] = t
                 if keep:
-                    self.activation_cache[n] = out[n]
-            while len(self.activation_cache) > self.max_cached:   # least recently used first
-                self.activation_cache.pop(next(iter(self.activation_cache)))
+                    self.activation_cache[n] = t
+            if keep:   # drop what no node after the cut reads any more
+                for t in [t for t in self.activation_cache
+                          if last.get(t, -1) <= cut and t not in names and prod.get(t, -1) < cut]:
+                    del self.activation_cache[t]
         return out
 
     def drop(self, names):

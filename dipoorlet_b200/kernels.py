@@ -279,3 +279,79 @@ def mix_drop(a, b, prob, seed, out=None):
                                  int(seed) & (2 ** 64 - 1), _stream()), "dpl_mix_drop_f32")
     _count()
     return y
+
+
+class GemmUnsupported(RuntimeError):
+    """The operands do not meet TMA's alignment rules; the caller keeps its other path."""
+
+
+_gemm_err = {}
+
+
+def gemm_tf32(a, a_major, lda, a_batch_stride, b, b_major, ldb, b_batch_stride, d, ldd, d_batch_stride,
+              M, N, K, batch=1, fold_batch=False, split_k=1, bias=None, bias_mode=0, relu=False):
+    """K6 dense tile (tcgen05 / TMA / TMEM). Raw-layout interface, see include/dpl_b200.h."""
+    dev = d.device
+    flag = _gemm_err.get(dev)
+    if flag is None:
+        flag = _gemm_err[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = lib().dpl_gemm_tf32(a.data_ptr(), int(a_major), int(lda), int(a_batch_stride), b.data_ptr(),
+                             int(b_major), int(ldb), int(b_batch_stride), d.data_ptr(), int(ldd),
+                             int(d_batch_stride), int(M), int(N), int(K), int(batch), int(bool(fold_batch)),
+                             int(split_k), _lib._ptr(bias), int(bias_mode), int(bool(relu)),
+                             flag.data_ptr(), _stream())
+    if st == 10003:
+        raise GemmUnsupported(lib().dpl_last_error().decode("utf-8", "replace"))
+    check(st, "dpl_gemm_tf32")
+    _count()
+    return d
+
+
+def gemm_check_errors(device=None):
+    """Synchronising check of the in-kernel timeout flag (tests / debugging)."""
+    for dev, flag in _gemm_err.items():
+        if device is None or dev == device:
+            if int(flag.item()) != 0:
+                flag.zero_()
+                raise RuntimeError("dpl_gemm_tf32: a pipeline wait timed out inside the kernel")
+
+
+def conv1x1_forward(x, w, bias=None, relu=False, out=None):
+    """O[img][co][hw] = W[co][ci] x X[img][ci][hw] (+ bias[co], relu), NCHW, stride 1."""
+    n, ci, hh, ww = x.shape
+    co = w.shape[0]
+    hw = hh * ww
+    o = torch.empty((n, co, hh, ww), dtype=torch.float32, device=x.device) if out is None else out
+    return gemm_tf32(w, 0, ci, 0, x, 1, hw, ci * hw, o, hw, co * hw, co, hw, ci, batch=n,
+                     bias=bias, bias_mode=1 if bias is not None else 0, relu=relu)
+
+
+def conv1x1_wgrad(go, x, split_k=None, out=None):
+    """dW[co][ci] = sum_img dO[img][co][hw] x X[img][ci][hw]^T."""
+    n, co, hh, ww = go.shape
+    ci = x.shape[1]
+    hw = hh * ww
+    tiles = ((co + 127) // 128) * ((ci + 127) // 128)
+    if split_k is None:
+        split_k = max(1, min(n, 148 // max(tiles, 1)))
+    dw = torch.zeros((co, ci), dtype=torch.float32, device=x.device) if out is None else out.zero_()
+    return gemm_tf32(go, 0, hw, co * hw, x, 0, hw, ci * hw, dw, ci, 0, co, ci, hw, batch=n,
+                     fold_batch=True, split_k=split_k)
+
+
+def conv1x1_dgrad(go, w, out=None):
+    """dX[img][ci][hw] = W[co][ci]^T x dO[img][co][hw]."""
+    n, co, hh, ww = go.shape
+    ci = w.shape[1]
+    hw = hh * ww
+    dx = torch.empty((n, ci, hh, ww), dtype=torch.float32, device=go.device) if out is None else out
+    return gemm_tf32(w, 1, ci, 0, go, 1, hw, co * hw, dx, hw, ci * hw, ci, hw, co, batch=n)
+
+
+def linear_forward(x, w, bias=None, relu=False):
+    """Y[n][out] = X[n][k] x W[out][k]^T (+ bias[out])."""
+    nrow, k = x.shape
+    out_f = w.shape[0]
+    y = torch.empty((nrow, out_f), dtype=torch.float32, device=x.device)
+    return gemm_tf32(x, 0, k, 0, w, 0, k, 0, y, out_f, 0, nrow, out_f, k, batch=1,
+                     bias=bias, bias_mode=2 if bias is not None else 0, relu=relu)

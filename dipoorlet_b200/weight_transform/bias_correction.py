@@ -51,10 +51,8 @@ def bias_correction(graph, act_clip_val, weight_clip_val, args):
         for g in (graph_bc, graph_q):
             g.set_initializer(name, new_bias)
         q_node = next(n for n in graph_q.graph.node if n.name == node.name)
-        q_cache.update_initializers([name], q_node)
-        fp_cache.drop([out])
-        q_cache.drop([out])
-        del fp_out, q_out
+        q_cache.update_initializers([name], q_node)   # drops q_out and everything downstream of it
+        del fp_out, q_out                             # fp tensors stay cached (LRU): the next layer starts there
     graph_bc.update_model()
     graph_bc.save_onnx_model('update_bias_model')
     return graph_bc

@@ -179,6 +179,27 @@ int dpl_recon_loss_f32(const float* d_o, const float* d_tgt, float* d_go, uint64
 int dpl_mix_drop_f32(const float* d_a, const float* d_b, float* d_y, uint64_t n, float prob,
                      uint64_t seed, void* stream);
 
+#define DPL_E_TIMEOUT 10004   /* a bounded in-kernel wait expired (reported through d_error_flag) */
+
+/* K6 dense tile — TF32 GEMM on tcgen05 tensor cores (TMA-staged operands, TMEM accumulators):
+ *   D[z][m][n] (+)= sum_k A[za][m][k] * B[z][k][n]  (+ bias, relu), fp32 in / out.
+ * Replaces the F.conv2d (1x1) / F.linear re-evaluation and their autograd gradients inside
+ * AdaQLayer.forward / learning_round_mask (weight_transform/ada_quant_layer.py:224-244,
+ * adaround.py:119-135), which torch runs on cuDNN with TF32 allowed.
+ *   a_major / b_major: 0 = K-major (element (row, k) at row * ld + k), 1 = MN-major (k * ld + row)
+ *   a_batch_stride = 0: A shared by all batch slices (weights)
+ *   fold_batch = 1: the batch is folded into K (weight gradient); split_k CTAs along it add
+ *                   their partial tiles atomically into D (caller zeroes D when split_k > 1)
+ *   bias_mode: 0 none, 1 per row m, 2 per column n
+ *   d_error_flag: int32 on the device, set to 1 if a pipeline wait timed out (never hangs)
+ * TMA needs 16-byte aligned bases and leading dimensions that are multiples of 4 floats;
+ * otherwise DPL_E_UNSUPPORTED is returned and the caller keeps its other path. */
+int dpl_gemm_tf32(const float* d_a, int a_major, long long lda, long long a_batch_stride,
+                  const float* d_b, int b_major, long long ldb, long long b_batch_stride,
+                  float* d_d, long long ldd, long long d_batch_stride, int M, int N, int K,
+                  int batch, int fold_batch, int split_k, const float* d_bias, int bias_mode,
+                  int relu, int* d_error_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,69 @@
+"""tcgen05 TF32 GEMM (dpl_gemm_tf32) against float64 matmul of TF32-truncated operands
+(kind::tf32 uses the top 19 bits of the fp32 pattern) and, loosely, plain fp32."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _tf32(t):
+    import torch
+    return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def _check(got, want64, scale):
+    err = (got.double() - want64).abs().max().item()
+    assert err <= 2e-5 * scale, (err, scale)
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 32), (200, 136, 100), (64, 1000, 2048), (300, 40, 36)])
+def test_linear_kk(dpl_built, shape):
+    import torch
+    from dipoorlet_b200 import kernels as K
+    m, n, k = shape
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn((m, k), device="cuda", generator=g)
+    w = torch.randn((n, k), device="cuda", generator=g)
+    b = torch.randn(n, device="cuda", generator=g)
+    y = K.linear_forward(x, w, b, relu=True)
+    K.gemm_check_errors()
+    want = torch.relu(_tf32(x).double() @ _tf32(w).double().t() + b.double())
+    _check(y, want, np.sqrt(k) * 4)
+    assert torch.allclose(y, torch.relu(x @ w.t() + b), rtol=2e-2, atol=2e-2 * np.sqrt(k))
+
+
+@pytest.mark.parametrize("dims", [(3, 64, 256, 56), (2, 96, 40, 28), (5, 256, 64, 14), (1, 8, 136, 12)])
+def test_conv1x1_forward_wgrad_dgrad(dpl_built, dims):
+    import torch
+    import torch.nn.functional as F
+    from dipoorlet_b200 import kernels as K
+    n, ci, co, hw = dims
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn((n, ci, hw, hw), device="cuda", generator=g)
+    w = torch.randn((co, ci), device="cuda", generator=g) * 0.1
+    b = torch.randn(co, device="cuda", generator=g)
+    go = torch.randn((n, co, hw, hw), device="cuda", generator=g)
+    xt, wt, got = _tf32(x).double(), _tf32(w).double(), _tf32(go).double()
+    o = K.conv1x1_forward(x, w, b)
+    K.gemm_check_errors()
+    want = torch.einsum("oc,nchw->nohw", wt, xt) + b.double().view(1, -1, 1, 1)
+    _check(o, want, np.sqrt(ci))
+    dw = K.conv1x1_wgrad(go, x)
+    K.gemm_check_errors()
+    want = torch.einsum("nohw,nchw->oc", got, xt)
+    _check(dw, want, np.sqrt(n * hw * hw) * 4)
+    dx = K.conv1x1_dgrad(go, w)
+    K.gemm_check_errors()
+    want = torch.einsum("oc,nohw->nchw", wt, got)
+    _check(dx, want, np.sqrt(co))
+    torch.backends.cudnn.allow_tf32 = False
+    assert torch.allclose(o, F.conv2d(x, w.view(co, ci, 1, 1), b), rtol=2e-2, atol=2e-2)
+
+
+def test_unsupported_alignment_is_reported(dpl_built):
+    import torch
+    from dipoorlet_b200 import kernels as K
+    x = torch.randn((2, 8, 7, 7), device="cuda")      # hw = 49: row stride not a multiple of 16 bytes
+    w = torch.randn((16, 8), device="cuda")
+    with pytest.raises(K.GemmUnsupported):
+        K.conv1x1_forward(x, w)

@@ -106,8 +106,13 @@ def test_learning_loop_matches_torch_autograd(dpl_built, relu, drop):
     w2 = torch.randn((5, 8, 1, 1), device=dev, generator=g) * 0.3
     attrs1 = {"dilations": [1, 1], "group": 1, "kernel_shape": [3, 3], "pads": [1, 1, 1, 1], "strides": [1, 1]}
     attrs2 = {"dilations": [1, 1], "group": 1, "kernel_shape": [1, 1], "pads": [0, 0, 0, 0], "strides": [2, 2]}
+    # the block input of the quantised graph differs from the fp one (as in the real flow):
+    # with identical inputs the initial loss is exactly zero (h(alpha0) = frac(w/s)) and the
+    # first Adam steps would be driven by rounding noise below eps, i.e. implementation chaos
+    x_fp = x
+    x = torch.round(x_fp / 0.1) * 0.1
     with torch.no_grad():
-        h = torch.nn.functional.conv2d(x, w1, b1, padding=1)
+        h = torch.nn.functional.conv2d(x_fp, w1, b1, padding=1)
         h = torch.relu(h) if relu else h
         tgt = torch.nn.functional.conv2d(h, w2, None, stride=2)
     total_iter = epochs * 2 * np.ceil(n / bs)
@@ -125,13 +130,20 @@ def test_learning_loop_matches_torch_autograd(dpl_built, relu, drop):
     reg = adaround_reg(total_iter)
     if drop:
         # different RNG streams: only check that it runs, stays finite and keeps the loss sane
-        loss = learning_round_mask(layers, x, tgt, reg, bs, epochs * 2, fp_in=x, drop=True)
+        loss = learning_round_mask(layers, x, tgt, reg, bs, epochs * 2, fp_in=x_fp, drop=True)
         assert np.isfinite(loss)
         return
     OA.learn(ref_layers, x, tgt, total_iter, bs, epochs * 2)
     loss = learning_round_mask(layers, x, tgt, reg, bs, epochs * 2)
     for ref, got in zip(ref_layers, layers):
-        d = (ref.round_mask.detach() - got.round_mask).abs().max().item()
+        # The largest weight of every channel has w/s = +-127 exactly, so h(alpha0) sits ON the
+        # clamp boundary 0: whether the gradient passes there depends on the last bit of
+        # sigmoid(), and Adam turns any non-zero gradient into a full +-lr step. Those
+        # (n_channels) elements are implementation-defined in the reference too: exclude them.
+        q = ref.weight / ref.scale
+        interior = ((q - q.floor()) > 1e-4) & ((q - q.floor()) < 1 - 1e-4)
+        d = (ref.round_mask.detach() - got.round_mask).abs()[interior].max().item()
         assert d < 2e-4, d
-        same = ((ref.round_mask.detach() >= 0) == (got.round_mask >= 0)).float().mean().item()
+        assert interior.float().mean().item() > 0.8
+        same = ((ref.round_mask.detach() >= 0) == (got.round_mask >= 0))[interior].float().mean().item()
         assert same > 0.999

@@ -8,7 +8,7 @@ STEPS="${@:-tests kbench bench ref launches ncu smoke}"
 for s in $STEPS; do
   echo "=== $s $(date +%T)" | tee -a gpurun_out/session.log
   case $s in
-    tests)   timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log ;;
+    tests)   timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; grep -E 'passed|failed|FAILED|Error' gpurun_out/pytest_gpu.log | tail -30 ;;
     kbench)  timeout 300 python tools/kbench.py --batch 32 > gpurun_out/kbench.log 2>&1; cat gpurun_out/kbench.log | tail -40 ;;
     bench)   timeout 600 python bench.py --steps 3 --warmup 3 --hist-variant ${HIST_VARIANT:-4} > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err ;;
     ref)     timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 1500 gpurun_out/bench_ref.json ;;
@@ -18,6 +18,8 @@ for s in $STEPS; do
     ncu)     timeout 600 ncu --set full --clock-control none --import-source on \
                  -k regex:'hist_lc|hist_lanecol|segstats_tiles|octav' -c 8 -f -o gpurun_out/prof_r1 \
                  python tools/kbench.py --batch 16 --quick > gpurun_out/ncu_run.log 2>&1; tail -3 gpurun_out/ncu_run.log ;;
+    configs) timeout 1200 python tools/run_configs.py --configs ${CONFIGS:-2 3 4 5} --ada-epoch ${ADA_EPOCH:-10} > gpurun_out/configs.log 2>&1; tail -8 gpurun_out/configs.log ;;
+    benchcb) DPL_CUDNN_BENCHMARK=1 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cudnn_benchmark.json 2> gpurun_out/bench_cb.err; tail -c 1500 gpurun_out/bench_cudnn_benchmark.json; tail -3 gpurun_out/bench_cb.err ;;
     smoke)   timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3 ;;
   esac
 done
