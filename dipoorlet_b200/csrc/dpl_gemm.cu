@@ -86,23 +86,28 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 // Shared-memory matrix descriptor (sm_100 format, cute::UMMA::SmemDescriptor): start >> 4 in
 // [0,14), leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in
 // [46,48), layout type in [61,64) (2 = 128-byte swizzle).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 // K-major, 128B swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart; K step = 32 bytes.
 __device__ __forceinline__ uint64_t desc_k_major(uint32_t tile, int kstep) {
-  return make_smem_desc(tile + kstep * (kUmmaK * 4), 16, 1024);
+  return make_smem_desc(tile + kstep * (kUmmaK * 4), 16, 1024, 2 /* SWIZZLE_128B */);
 }
-// MN-major, 128B swizzle: the tile is 4 column blocks of [kBK k-rows][32 elements = 128 bytes];
-// 128-byte chunks along MN are 4096 bytes apart (LBO), 8-row groups along K 1024 bytes (SBO).
+// MN-major: 32-bit operands only exist in the "128-byte swizzle, 32-byte atom" layout
+// (UMMA LayoutType 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; cutlass sm100_common.inl: "for
+// mn-major tf32 operands, SW128_32B is the only available smem layout"). The tile is 4 column
+// blocks of [kBK k-rows][32 elements = 128 bytes]: 128-byte chunks along MN are 4096 bytes
+// apart (LBO); the swizzle atom spans 4 k-rows, so groups along K are 512 bytes apart (SBO);
+// one K = 8 instruction covers two groups = 1024 bytes.
 __device__ __forceinline__ uint64_t desc_mn_major(uint32_t tile, int kstep) {
-  return make_smem_desc(tile + kstep * 1024, kBK * 128, 1024);
+  return make_smem_desc(tile + kstep * 1024, kBK * 128, 512, 1 /* SWIZZLE_128B_BASE32B */);
 }
 
 template <bool A_MN, bool B_MN>
@@ -245,17 +250,29 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (m < p.M) {
+        const int nc = n0 + c * 32;
+        float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c * 32 + j;
-          if (n < p.N) {
-            float v = __uint_as_float(r[j]) + bias_m;
-            if (p.bias_mode == 2) v += p.bias[n];
-            if (p.relu) v = fmaxf(v, 0.f);
-            if (p.atomic_out)
-              atomicAdd(drow + n, v);
-            else
-              drow[n] = v;
+          v[j] = __uint_as_float(r[j]) + bias_m;
+          if (p.bias_mode == 2 && nc + j < p.N) v[j] += p.bias[nc + j];
+          if (p.relu) v[j] = fmaxf(v[j], 0.f);
+        }
+        float* dst = drow + nc;
+        if (!p.atomic_out && nc + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+          // the thread owns 128 contiguous bytes of its output row: 8 x 16-byte stores
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (nc + j < p.N) {
+              if (p.atomic_out)
+                atomicAdd(dst + j, v[j]);
+              else
+                dst[j] = v[j];
+            }
           }
         }
       }
@@ -293,7 +310,7 @@ EncodeTiledFn encode_fn() {
 
 // 3-D fp32 tensor (inner, outer, batch) with a [32 x box_outer x 1] box and 128-byte swizzle.
 int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t batch,
-             uint64_t outer_stride_elems, uint64_t batch_stride_elems, uint32_t box_outer) {
+             uint64_t outer_stride_elems, uint64_t batch_stride_elems, uint32_t box_outer, bool mn_major) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -309,7 +326,9 @@ int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer
   cuuint32_t box[3] = {32, box_outer, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -336,14 +355,14 @@ extern "C" int dpl_gemm_tf32(const float* d_a, int a_major, long long lda, long 
   int st;
   const uint64_t a_z = a_batch_stride ? (uint64_t)batch : 1;
   if (a_major == 0)
-    st = make_map(&tmA, d_a, K, M, a_z, lda, a_batch_stride, kBM);
+    st = make_map(&tmA, d_a, K, M, a_z, lda, a_batch_stride, kBM, false);
   else
-    st = make_map(&tmA, d_a, M, K, a_z, lda, a_batch_stride, kBK);
+    st = make_map(&tmA, d_a, M, K, a_z, lda, a_batch_stride, kBK, true);
   if (st) return st;
   if (b_major == 0)
-    st = make_map(&tmB, d_b, K, N, batch, ldb, b_batch_stride, kBN);
+    st = make_map(&tmB, d_b, K, N, batch, ldb, b_batch_stride, kBN, false);
   else
-    st = make_map(&tmB, d_b, N, K, batch, ldb, b_batch_stride, kBK);
+    st = make_map(&tmB, d_b, N, K, batch, ldb, b_batch_stride, kBK, true);
   if (st) return st;
 
   GemmParams p;

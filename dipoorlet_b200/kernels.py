@@ -355,3 +355,19 @@ def linear_forward(x, w, bias=None, relu=False):
     y = torch.empty((nrow, out_f), dtype=torch.float32, device=x.device)
     return gemm_tf32(x, 0, k, 0, w, 0, k, 0, y, out_f, 0, nrow, out_f, k, batch=1,
                      bias=bias, bias_mode=2 if bias is not None else 0, relu=relu)
+
+
+def linear_wgrad(go, x):
+    """dW[out][in] = dY[n][out]^T x X[n][in] (both operands MN-major: n is the K index)."""
+    nrow, out_f = go.shape
+    in_f = x.shape[1]
+    dw = torch.empty((out_f, in_f), dtype=torch.float32, device=x.device)
+    return gemm_tf32(go, 1, out_f, 0, x, 1, in_f, 0, dw, in_f, 0, out_f, in_f, nrow, batch=1)
+
+
+def linear_dgrad(go, w):
+    """dX[n][in] = dY[n][out] x W[out][in]."""
+    nrow, out_f = go.shape
+    in_f = w.shape[1]
+    dx = torch.empty((nrow, in_f), dtype=torch.float32, device=go.device)
+    return gemm_tf32(go, 0, out_f, 0, w, 1, in_f, 0, dx, in_f, 0, nrow, in_f, out_f, batch=1)

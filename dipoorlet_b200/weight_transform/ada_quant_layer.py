@@ -14,6 +14,8 @@ STAND-IN NOTICE: the dense contraction is issued through torch.ops.aten.convolut
 convolution_backward (true fp32); a tcgen05 implicit-GEMM tile is the planned replacement
 (DESIGN.md, "what comes next").
 """
+import os
+
 import numpy as np
 import torch
 
@@ -106,7 +108,35 @@ class AdaQLayer:
         return w.transpose(0, 1) if self.type == 'ConvTranspose' else w
 
     # ---- forward / backward of the dense op (stand-in: cuDNN / cuBLAS, true fp32) --------
+    def _tensor_core_ok(self, x):
+        """tcgen05 TF32 tile (libdpl_b200 dpl_gemm_tf32) for the shapes TMA can address: 1x1
+        stride-1 ungrouped convolutions with C_in and H*W multiples of 4, and Gemm layers with
+        K a multiple of 4. TF32 is what the reference's torch conv uses by default
+        (cudnn.allow_tf32 = True). DPL_TCGEN05=0 keeps everything on the fp32 library path."""
+        if os.environ.get("DPL_TCGEN05", "1") == "0":
+            return False
+        if getattr(self, "_tc_disabled", False):
+            return False
+        if self.type == 'Gemm':   # K and the output width are leading dimensions of TMA operands
+            return (x.dim() == 2 and x.shape[1] % 4 == 0 and self.weight.shape[0] % 4 == 0
+                    and x.is_contiguous())
+        if self.type != 'Conv' or x.dim() != 4 or not x.is_contiguous():
+            return False
+        k = self.weight.shape[2:]
+        return (list(k) == [1, 1] and self.stride == [1, 1] and self.padding == [0, 0]
+                and self.dilation == [1, 1] and self.groups == 1 and x.shape[1] % 4 == 0
+                and (x.shape[2] * x.shape[3]) % 4 == 0)
+
     def dense_forward(self, x, w):
+        self._tc = self._tensor_core_ok(x)
+        if self._tc:
+            try:
+                if self.type == 'Gemm':
+                    return K.linear_forward(x, w, self.bias)
+                return K.conv1x1_forward(x, w.view(w.shape[0], w.shape[1]), self.bias)
+            except K.GemmUnsupported:     # e.g. a mis-aligned slice: keep this layer on the library path
+                self._tc = False
+                self._tc_disabled = True
         if self.type == 'Gemm':
             return torch.nn.functional.linear(x, w, self.bias)
         return torch.ops.aten.convolution(x, self._w_for_op(w), self.bias, self.stride, self.padding,
@@ -114,6 +144,16 @@ class AdaQLayer:
                                           self.output_padding, self.groups)
 
     def dense_backward(self, x, w, go, need_dx):
+        if getattr(self, "_tc", False):
+            try:
+                if self.type == 'Gemm':
+                    return (K.linear_dgrad(go, w) if need_dx else None), K.linear_wgrad(go, x)
+                w2 = w.view(w.shape[0], w.shape[1])
+                gw = K.conv1x1_wgrad(go, x).view_as(w)
+                return (K.conv1x1_dgrad(go, w2) if need_dx else None), gw
+            except K.GemmUnsupported:
+                self._tc = False
+                self._tc_disabled = True
         if self.type == 'Gemm':
             gw = go.t() @ x
             gx = go @ w if need_dx else None

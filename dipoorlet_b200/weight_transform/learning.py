@@ -5,6 +5,8 @@ Reference: torch autograd + torch.optim.Adam under DistributedDataParallel, one 
 iteration = dozens of small kernels. Here: a fixed launch sequence per iteration, no
 autograd graph, alpha/m/v updated in place by one fused kernel, gradient averaging over
 ranks by one NCCL all-reduce of dL/dW per layer (DDP semantics)."""
+import os
+
 import numpy as np
 import torch
 
@@ -23,6 +25,27 @@ def learning_round_mask(layers, q_in, tgt, reg, batch_size, max_epoch, fp_in=Non
     q_in / fp_in: block input from the quantised / fp graph, tgt: fp block output (after the
     trailing Relu when there is one), all float32 CUDA tensors [n, ...] resident in HBM.
     Returns the last mini-batch loss (as the reference logs it)."""
+    # Numerics of the re-evaluation: the reference's F.conv2d runs with torch's default
+    # cudnn.allow_tf32 = True and F.linear in true fp32 (SURVEY.md A-8). Same here: TF32 tensor
+    # cores for the convolutions (tcgen05 tile for 1x1, cuDNN for the rest), fp32 for Gemm on
+    # the library path. DPL_RECON_TF32=0 forces fp32 everywhere (and the tcgen05 tile off).
+    tf32 = os.environ.get("DPL_RECON_TF32", "1") != "0"
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, os.environ.get("DPL_TCGEN05"))
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    if not tf32:
+        os.environ["DPL_TCGEN05"] = "0"
+    try:
+        return _learn(layers, q_in, tgt, reg, batch_size, max_epoch, fp_in, drop, log_every, head, seed)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved[0], saved[1]
+        if saved[2] is None:
+            os.environ.pop("DPL_TCGEN05", None)
+        else:
+            os.environ["DPL_TCGEN05"] = saved[2]
+
+
+def _learn(layers, q_in, tgt, reg, batch_size, max_epoch, fp_in, drop, log_every, head, seed):
     n = q_in.shape[0]
     n_batches = int(np.ceil(n / batch_size))
     world = dist_helper.get_world_size()

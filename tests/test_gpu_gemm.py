@@ -30,6 +30,12 @@ def test_linear_kk(dpl_built, shape):
     want = torch.relu(_tf32(x).double() @ _tf32(w).double().t() + b.double())
     _check(y, want, np.sqrt(k) * 4)
     assert torch.allclose(y, torch.relu(x @ w.t() + b), rtol=2e-2, atol=2e-2 * np.sqrt(k))
+    go = torch.randn((m, n), device="cuda", generator=g)
+    dw = K.linear_wgrad(go, x)
+    dx = K.linear_dgrad(go, w)
+    K.gemm_check_errors()
+    _check(dw, _tf32(go).double().t() @ _tf32(x).double(), np.sqrt(m) * 4)
+    _check(dx, _tf32(go).double() @ _tf32(w).double(), np.sqrt(n) * 4)
 
 
 @pytest.mark.parametrize("dims", [(3, 64, 256, 56), (2, 96, 40, 28), (5, 256, 64, 14), (1, 8, 136, 12)])

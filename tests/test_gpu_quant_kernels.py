@@ -87,7 +87,7 @@ def test_adaround_init_and_weight(dpl_built):
 
 
 @pytest.mark.parametrize("relu,drop", [(True, False), (False, False), (True, True)])
-def test_learning_loop_matches_torch_autograd(dpl_built, relu, drop):
+def test_learning_loop_matches_torch_autograd(dpl_built, relu, drop, monkeypatch):
     """A 2-layer block (conv3x3 -> [relu] -> conv1x1) for 30 iterations: the fused launch
     sequence must track torch autograd + torch.optim.Adam (same device, fp32)."""
     import torch
@@ -95,6 +95,7 @@ def test_learning_loop_matches_torch_autograd(dpl_built, relu, drop):
     from dipoorlet_b200.weight_transform.ada_quant_layer import AdaQLayer, adaround_reg
     from dipoorlet_b200.weight_transform.learning import learning_round_mask
     from oracle import adaround as OA
+    monkeypatch.setenv("DPL_RECON_TF32", "0")   # fp32 vs fp32: this test is about the update rule
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     dev = torch.device("cuda")
