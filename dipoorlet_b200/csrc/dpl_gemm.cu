@@ -15,7 +15,7 @@
 //
 // One CTA = one 128 x 128 output tile, 4 warps: warp 0 / lane 0 issues TMA, warp 1 / lane 0
 // issues the MMAs, warp 2 owns the TMEM allocation, all four warps run the epilogue (TMEM lane
-// quarter = warp id). 4-stage shared-memory ring (32 KB per stage) with full/empty mbarriers;
+// quarter = warp id). 3-stage shared-memory ring (32 KB per stage, two CTAs per SM) with full/empty mbarriers;
 // tcgen05.commit releases a stage when the MMAs that read it have retired. Every mbarrier wait
 // is bounded in time: a protocol error surfaces as DPL_E_TIMEOUT instead of a hung GPU.
 
@@ -28,7 +28,7 @@ namespace dpl {
 namespace {
 
 constexpr int kBM = 128, kBN = 128, kBK = 32;       // tile; kBK floats = one 128-byte swizzle row
-constexpr int kStages = 4;
+constexpr int kStages = 3;                           // 96 KB: two CTAs per SM overlap epilogue and main loop
 constexpr int kTileBytes = kBM * kBK * 4;           // 16 KB per operand per stage
 constexpr int kStageBytes = 2 * kTileBytes;
 constexpr int kUmmaK = 8;                           // tf32: 32 bytes of K per instruction
@@ -111,7 +111,7 @@ __device__ __forceinline__ uint64_t desc_mn_major(uint32_t tile, int kstep) {
 }
 
 template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
