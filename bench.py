@@ -278,7 +278,10 @@ def run_ours(args):
     passes = 1 if resident_used["v"] else 2   # recompute mode re-sends the images for pass 2
     h2d_per_step = passes * images.nbytes * world
 
+    if world > 1:
+        dist.barrier()
     if rank != 0:
+        dist.destroy_process_group()
         return
     elems_per_img = W.blob_elements(W.resnet50_blob_shapes())
     line = {
@@ -307,6 +310,8 @@ def run_ours(args):
         except Exception as e:  # the baseline must not take the measurement down
             line["cpu_baseline"] = {"error": repr(e)}
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

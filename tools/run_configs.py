@@ -38,7 +38,10 @@ def run(cfg, n_img, ada_epoch, out):
           5: dict(model="r50", act_quant="hist", brecq=True, drop=True)}[cfg]
     mname = kw.pop("model")
     model = W.build_resnet50(seed=0) if mname == "r50" else W.build_mobilenetv2(seed=0)
-    tmp = tempfile.mkdtemp(prefix=f"dpl_cfg{cfg}_")
+    tmp = [tempfile.mkdtemp(prefix=f"dpl_cfg{cfg}_") if rank == 0 else None]
+    if world > 1:   # one output directory for all ranks (the CLI gets it from -O)
+        torch.distributed.broadcast_object_list(tmp, src=0)
+    tmp = tmp[0]
     graph = ONNXGraph(model, tmp, "trt")
     images = W.synthetic_images(n_img, seed=0, start=rank * n_img)[:, 0]
     args = make_args(input_dir=fwd.ArrayInput({"input": images}, start=rank * n_img), data_num=n_img * world,
@@ -92,6 +95,8 @@ def main():
         run(cfg, n, a.ada_epoch, a.out)
         fwd._SESSIONS.clear()
         torch.cuda.empty_cache()
+    if torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
