@@ -78,6 +78,21 @@ def _device_of(args):
     return torch.device(forced) if forced else torch.device("cuda", getattr(args, "local_rank", 0) or 0)
 
 
+def _engine_for(onnx_graph, dev):
+    """One Engine (= one upload of the weights, 100 MB for ResNet-50) per graph object and
+    device, reused by successive calibration calls on the same graph."""
+    cache = onnx_graph.__dict__.setdefault("_dpl_engines", {})
+    eng = cache.get(str(dev))
+    version = getattr(onnx_graph, "_init_version", 0)
+    if eng is None or eng.nodes != list(onnx_graph.model.graph.nodes):
+        eng = cache[str(dev)] = Engine(onnx_graph, dev, _unit_test_cpu=dev.type != "cuda")
+        eng._init_version = version
+    elif getattr(eng, "_init_version", 0) != version:     # weights were edited since the upload
+        eng.refresh_initializers()
+        eng._init_version = version
+    return eng
+
+
 def shard_range(args):
     """forward_net.py:207-209: contiguous shard, floor division (the tail is dropped)."""
     rank_num = args.data_num // args.world_size
@@ -109,7 +124,7 @@ class CalibrationSession:
         self.args = args
         dev = _device_of(args)
         self.device = dev
-        self.engine = engine or Engine(onnx_graph, dev, _unit_test_cpu=dev.type != "cuda")
+        self.engine = engine or _engine_for(onnx_graph, dev)
         self.names = self.engine.blob_names()
         self.n_stats = len(self.names)
         self.st, self.ed = shard_range(args)

@@ -361,6 +361,7 @@ class ONNXGraph:
     # -- mutation ---------------------------------------------------------------
     def set_initializer(self, name, value, raw=True):
         self.model.graph.initializers[name] = np.asarray(value)
+        self._init_version = getattr(self, "_init_version", 0) + 1   # cached engines re-upload
         self.prepare_initializer()
 
     def del_initializer(self, name):
@@ -395,6 +396,12 @@ class ONNXGraph:
     def update_model(self):
         self.set_index()
         self.prepare_initializer()
+
+    def __deepcopy__(self, memo):
+        new = ONNXGraph()
+        new.copy_from(self)
+        new.name_idx_map = dict(self.name_idx_map)
+        return new
 
     def copy_from(self, src):
         self.model = copy.deepcopy(src.model)
