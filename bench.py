@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=IMAGES_PER_GPU, help="images per GPU")
-    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--hist-variant", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -300,7 +300,12 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "K2 dpl_hist_abs_f32 variant %d" % args.hist_variant, "achieved": achieved, "peak": peak,
                      "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured"
                      else "fallback 6.65 TB/s", "unit": "GB/s", "frac": achieved / peak if peak else None,
-                     "traffic": None, "launches_timed": len(hist_ms),
+                     # dram__bytes_read + dram__bytes_write of this kernel from one `ncu --set full` capture
+                     # (profiles/r1_hist_v7_batch32_ncu.md: 3.4125 GB for 3.4046 GB algorithmic), scaled
+                     # to this run's bytes per launch
+                     "traffic": (1.00232 * float(np.mean(hist_bytes))) if hist_bytes else None,
+                     "traffic_source": "ncu capture at batch 32, scaled by bytes per launch",
+                     "launches_timed": len(hist_ms),
                      "bytes_per_launch": float(np.mean(hist_bytes)) if hist_bytes else 0,
                      "ms_per_launch": float(np.mean(hist_ms)) if hist_ms else None},
     }

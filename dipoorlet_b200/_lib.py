@@ -57,13 +57,15 @@ SIGNATURES = {
                                          _c_int, _c_vp, _c_vp]),
     "dpl_adaround_step_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_u64, _c_flt, _c_flt, _c_flt,
                                        _c_flt, _c_flt, _c_flt, _c_flt, _c_flt, _c_int, _c_flt,
-                                       _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
+                                       _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "dpl_recon_act_f32": (_c_int, [_c_vp, _c_vp, _c_u64, _c_int, _c_int, _c_flt, _c_flt, _c_flt, _c_flt,
-                                   _c_u64, _c_vp]),
+                                   _c_u64, _c_vp, _c_vp]),
     "dpl_recon_act_bwd_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_u64, _c_int, _c_int, _c_flt, _c_flt,
-                                       _c_flt, _c_flt, _c_u64, _c_vp]),
+                                       _c_flt, _c_flt, _c_u64, _c_vp, _c_vp]),
     "dpl_recon_loss_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_u64, _c_int, _c_int, _c_flt, _c_flt, _c_flt,
-                                    _c_flt, _c_u64, _c_flt, _c_vp, _c_vp]),
+                                    _c_flt, _c_u64, _c_flt, _c_vp, _c_vp, _c_vp]),
+    "dpl_recon_schedule": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_dbl, _c_dbl,
+                                    _c_dbl, _c_u64, _c_vp]),
     "dpl_gemm_tf32": (_c_int, [_c_vp, _c_int, ctypes.c_longlong, ctypes.c_longlong, _c_vp, _c_int,
                                ctypes.c_longlong, ctypes.c_longlong, _c_vp, ctypes.c_longlong,
                                ctypes.c_longlong, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp,

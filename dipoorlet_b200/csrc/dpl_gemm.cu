@@ -396,10 +396,14 @@ extern "C" int dpl_gemm_tf32(const float* d_a, int a_major, long long lda, long 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define DPL_GEMM_LAUNCH(AMN, BMN)                                                                      \
   do {                                                                                                 \
-    int e = cuda_status(cudaFuncSetAttribute(gemm_tf32_kernel<AMN, BMN>,                               \
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),  \
-                        "cudaFuncSetAttribute(gemm_tf32_kernel)");                                     \
-    if (e) return e;                                                                                   \
+    static bool attr_done = false; /* one device per process (one rank per GPU) */                    \
+    if (!attr_done) {                                                                                  \
+      int e = cuda_status(cudaFuncSetAttribute(gemm_tf32_kernel<AMN, BMN>,                             \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),\
+                          "cudaFuncSetAttribute(gemm_tf32_kernel)");                                   \
+      if (e) return e;                                                                                 \
+      attr_done = true;                                                                                \
+    }                                                                                                  \
     gemm_tf32_kernel<AMN, BMN><<<grid, kGemmThreads, smem, s>>>(tmA, tmB, p);                          \
   } while (0)
   if (a_major == 0 && b_major == 0)

@@ -96,19 +96,16 @@ octav_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_t n_segment
         // stream the sub-range from the blob; keep |x| > s
         uint64_t wr = 0;
         float blk = 0.f;  // float partial of one macro-step, folded into the double sum
+        uint32_t le_cnt = 0;  // per-lane count(|x| <= s); explicit so that NaN behaves as in NumPy
+        const unsigned lt_mask = (1u << lane) - 1u;
         auto visit = [&](float a, bool in) {
           const bool g = in && (a > s);
-          const bool l = in && (a <= s);
           const unsigned mg = __ballot_sync(0xffffffffu, g);
-          const unsigned ml = __ballot_sync(0xffffffffu, l);
           if (g) {
             blk += a;
-            wout[wr + __popc(mg & ((1u << lane) - 1u))] = a;
+            wout[wr + __popc(mg & lt_mask)] = a;
           }
-          if (lane == 0) {
-            acc.gt += __popc(mg);
-            acc.le += __popc(ml);
-          }
+          le_cnt += (in && (a <= s)) ? 1u : 0u;
           wr += __popc(mg);
         };
         uint64_t i = w0;
@@ -146,28 +143,28 @@ octav_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_t n_segment
         cnt = wr;
         thr = s;
         have = true;
+        if (lane == 0) acc.gt = wr;
+        acc.le = le_cnt;
       } else {
         // survivors only, compacted in place: a write never passes the rows already read
         uint64_t wr = 0;
         float blk = 0.f;
+        const unsigned lt_mask = (1u << lane) - 1u;
         for (uint64_t i = 0; i < cnt; i += 256) {  // 8 rows of 32 in flight
           float a[8];
-          bool in[8];
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
             const uint64_t j = i + r * 32 + lane;
-            in[r] = j < cnt;
-            a[r] = in[r] ? __ldcg(wout + j) : 0.f;
+            a[r] = (j < cnt) ? __ldcg(wout + j) : 0.f;   // 0 never survives (s > 0)
           }
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
-            const bool g = in[r] && (a[r] > s);
+            const bool g = a[r] > s;
             const unsigned mg = __ballot_sync(0xffffffffu, g);
             if (g) {
               blk += a[r];
-              wout[wr + __popc(mg & ((1u << lane) - 1u))] = a[r];
+              wout[wr + __popc(mg & lt_mask)] = a[r];
             }
-            if (lane == 0) acc.gt += __popc(mg);
             wr += __popc(mg);
           }
           acc.sum += (double)blk;
@@ -176,6 +173,7 @@ octav_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_t n_segment
         }
         cnt = wr;
         thr = s;
+        if (lane == 0) acc.gt = wr;
       }
       const bool was_rescan = rescan;
       block_reduce(acc, s_sum, s_gt, s_le);

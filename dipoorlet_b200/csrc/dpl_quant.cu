@@ -192,7 +192,12 @@ adaround_step_kernel(const float* __restrict__ grad_w, const float* __restrict__
                      float qmin, float qmax, float beta, float reg_alpha, float lr, float b1,
                      float b2, float eps, float bc1, float bc2_sqrt, float grad_scale,
                      float* __restrict__ alpha, float* __restrict__ m, float* __restrict__ v,
-                     double* __restrict__ reg_out) {
+                     double* __restrict__ reg_out, const float* __restrict__ sched) {
+  if (sched) {   // per-iteration scalars from device memory (CUDA-graph replay)
+    beta = sched[0];
+    bc1 = sched[1];
+    bc2_sqrt = sched[2];
+  }
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   double reg_acc = 0.0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -316,7 +321,7 @@ extern "C" int dpl_adaround_step_f32(const float* d_grad_w, const float* d_wfloo
                                      float qmin, float qmax, float beta, float reg_alpha, float lr,
                                      float b1, float b2, float eps, int step, float grad_scale,
                                      float* d_alpha, float* d_m, float* d_v, double* d_reg,
-                                     void* stream) {
+                                     const float* d_sched, void* stream) {
   DPL_REQUIRE(d_grad_w && d_wfloor && d_scale && d_alpha && d_m && d_v, "null pointer");
   DPL_REQUIRE(n_channels >= 1 && inner >= 1 && step >= 1, "bad arguments");
   const uint64_t n = (uint64_t)n_channels * inner;
@@ -325,7 +330,7 @@ extern "C" int dpl_adaround_step_f32(const float* d_grad_w, const float* d_wfloo
   const double bc2 = 1.0 - pow((double)b2, (double)step);
   adaround_step_kernel<<<ew_grid(n, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_grad_w, d_wfloor, d_scale, n_channels, inner, n, qmin, qmax, beta, reg_alpha, lr, b1, b2,
-      eps, (float)bc1, (float)sqrt(bc2), grad_scale, d_alpha, d_m, d_v, d_reg);
+      eps, (float)bc1, (float)sqrt(bc2), grad_scale, d_alpha, d_m, d_v, d_reg, d_sched);
   DPL_LAUNCH_CHECK("adaround_step_kernel");
   return 0;
 }

@@ -26,6 +26,9 @@ __device__ __forceinline__ float u01(uint64_t seed, uint64_t i) {
   return (float)(z >> 40) * (1.0f / 16777216.0f);
 }
 
+// Per-iteration scalars live in device memory so that one captured CUDA graph can be replayed
+// for every iteration of the optimisation loop:
+//   sched[0] = beta(t), sched[1] = 1 - b1^(t+1), sched[2] = sqrt(1 - b2^(t+1)), seeds[l] per layer
 struct ActCfg {
   int relu;        // apply max(o, 0)
   int quant;       // apply fake-quant (per-tensor scale, symmetric [qmin, qmax])
@@ -55,7 +58,9 @@ __device__ __forceinline__ float act_fwd(float o, uint64_t i, const ActCfg& c, b
 }
 
 __global__ void __launch_bounds__(256)
-recon_act_kernel(const float* __restrict__ o, float* __restrict__ y, uint64_t n, ActCfg c) {
+recon_act_kernel(const float* __restrict__ o, float* __restrict__ y, uint64_t n, ActCfg c,
+                 const unsigned long long* __restrict__ seed_ptr) {
+  if (seed_ptr) c.seed = *seed_ptr;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     bool pass;
@@ -65,7 +70,9 @@ recon_act_kernel(const float* __restrict__ o, float* __restrict__ y, uint64_t n,
 
 __global__ void __launch_bounds__(256)
 recon_act_bwd_kernel(const float* __restrict__ o, const float* __restrict__ gy,
-                     float* __restrict__ go, uint64_t n, ActCfg c) {
+                     float* __restrict__ go, uint64_t n, ActCfg c,
+                     const unsigned long long* __restrict__ seed_ptr) {
+  if (seed_ptr) c.seed = *seed_ptr;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     bool pass;
@@ -78,7 +85,8 @@ recon_act_bwd_kernel(const float* __restrict__ o, const float* __restrict__ gy,
 __global__ void __launch_bounds__(256)
 recon_loss_kernel(const float* __restrict__ o, const float* __restrict__ tgt,
                   float* __restrict__ go, uint64_t n, ActCfg c, float inv_count,
-                  double* __restrict__ loss) {
+                  double* __restrict__ loss, const unsigned long long* __restrict__ seed_ptr) {
+  if (seed_ptr) c.seed = *seed_ptr;
   __shared__ double s_red[8];
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   double acc = 0.0;
@@ -105,6 +113,29 @@ recon_loss_kernel(const float* __restrict__ o, const float* __restrict__ tgt,
     for (int w = 0; w < 8; ++w) t += s_red[w];
     atomicAdd(loss, t * (double)inv_count);
   }
+}
+
+// One thread: the schedule of iteration t = *iter (TempDecay, ada_quant_layer.py:117-130; Adam
+// bias corrections; per-layer mask seeds), then t += 1.
+__global__ void recon_schedule_kernel(int* __restrict__ iter, float* __restrict__ sched,
+                                      unsigned long long* __restrict__ seeds, int n_seeds, double t_max,
+                                      double rel_start, double start_b, double end_b, double b1, double b2,
+                                      unsigned long long seed_base) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int t = *iter;
+  const double start_decay = rel_start * t_max;
+  double beta = 0.0;
+  if (!((double)t < start_decay)) {
+    const double rel_t = ((double)t - start_decay) / (t_max - start_decay);
+    beta = end_b + 0.5 * (start_b - end_b) * (1.0 + cos(rel_t * 3.141592653589793));
+  }
+  sched[0] = (float)beta;
+  sched[1] = (float)(1.0 - pow(b1, (double)(t + 1)));
+  sched[2] = (float)sqrt(1.0 - pow(b2, (double)(t + 1)));
+  for (int l = 0; l < n_seeds; ++l)
+    seeds[l] = (seed_base * 1000003ull + (unsigned long long)t * 131ull + (unsigned long long)l * 7ull + 12345ull) &
+               0x7FFFFFFFFFFFFFFFull;
+  *iter = t + 1;
 }
 
 __global__ void __launch_bounds__(256)
@@ -143,22 +174,23 @@ using namespace dpl;
 
 extern "C" int dpl_recon_act_f32(const float* d_o, float* d_y, uint64_t n, int relu, int quant,
                                  float scale, float qmin, float qmax, float prob, uint64_t seed,
-                                 void* stream) {
+                                 const unsigned long long* d_seed, void* stream) {
   DPL_REQUIRE(d_o && d_y, "null pointer");
   if (n == 0) return 0;
   recon_act_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_o, d_y, n, make_cfg(relu, quant, scale, qmin, qmax, prob, seed));
+      d_o, d_y, n, make_cfg(relu, quant, scale, qmin, qmax, prob, seed), d_seed);
   DPL_LAUNCH_CHECK("recon_act_kernel");
   return 0;
 }
 
 extern "C" int dpl_recon_act_bwd_f32(const float* d_o, const float* d_gy, float* d_go, uint64_t n,
                                      int relu, int quant, float scale, float qmin, float qmax,
-                                     float prob, uint64_t seed, void* stream) {
+                                     float prob, uint64_t seed, const unsigned long long* d_seed,
+                                     void* stream) {
   DPL_REQUIRE(d_o && d_gy && d_go, "null pointer");
   if (n == 0) return 0;
   recon_act_bwd_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_o, d_gy, d_go, n, make_cfg(relu, quant, scale, qmin, qmax, prob, seed));
+      d_o, d_gy, d_go, n, make_cfg(relu, quant, scale, qmin, qmax, prob, seed), d_seed);
   DPL_LAUNCH_CHECK("recon_act_bwd_kernel");
   return 0;
 }
@@ -166,11 +198,12 @@ extern "C" int dpl_recon_act_bwd_f32(const float* d_o, const float* d_gy, float*
 extern "C" int dpl_recon_loss_f32(const float* d_o, const float* d_tgt, float* d_go, uint64_t n,
                                   int relu, int quant, float scale, float qmin, float qmax,
                                   float prob, uint64_t seed, float inv_count, double* d_loss,
-                                  void* stream) {
+                                  const unsigned long long* d_seed, void* stream) {
   DPL_REQUIRE(d_o && d_tgt && d_go, "null pointer");
   if (n == 0) return 0;
   recon_loss_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_o, d_tgt, d_go, n, make_cfg(relu, quant, scale, qmin, qmax, prob, seed), inv_count, d_loss);
+      d_o, d_tgt, d_go, n, make_cfg(relu, quant, scale, qmin, qmax, prob, seed), inv_count, d_loss,
+      d_seed);
   DPL_LAUNCH_CHECK("recon_loss_kernel");
   return 0;
 }
@@ -182,5 +215,16 @@ extern "C" int dpl_mix_drop_f32(const float* d_a, const float* d_b, float* d_y, 
   mix_drop_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_a, d_b, d_y, n, prob,
                                                                              seed);
   DPL_LAUNCH_CHECK("mix_drop_kernel");
+  return 0;
+}
+
+extern "C" int dpl_recon_schedule(int* d_iter, float* d_sched, unsigned long long* d_seeds, int n_seeds,
+                                  double t_max, double rel_start, double start_b, double end_b, double b1,
+                                  double b2, uint64_t seed_base, void* stream) {
+  DPL_REQUIRE(d_iter && d_sched, "null pointer");
+  DPL_REQUIRE(n_seeds == 0 || d_seeds, "null seeds");
+  recon_schedule_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_iter, d_sched, d_seeds, n_seeds, t_max, rel_start, start_b, end_b, b1, b2, seed_base);
+  DPL_LAUNCH_CHECK("recon_schedule_kernel");
   return 0;
 }

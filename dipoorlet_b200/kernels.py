@@ -226,48 +226,49 @@ def adaround_weight(wfloor, alpha, scale, qmin, qmax, soft, out=None):
 
 
 def adaround_step(grad_w, wfloor, scale, qmin, qmax, beta, alpha, m, v, step, reg_alpha=0.01,
-                  lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0, reg_out=None):
+                  lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0, reg_out=None, sched=None):
     c = scale.numel()
     inner = wfloor.numel() // c
     check(lib().dpl_adaround_step_f32(grad_w.data_ptr(), wfloor.data_ptr(), scale.data_ptr(), c,
                                       inner, float(qmin), float(qmax), float(beta),
                                       float(reg_alpha), float(lr), float(b1), float(b2), float(eps),
                                       int(step), float(grad_scale), alpha.data_ptr(), m.data_ptr(),
-                                      v.data_ptr(), _lib._ptr(reg_out), _stream()),
+                                      v.data_ptr(), _lib._ptr(reg_out), _lib._ptr(sched), _stream()),
           "dpl_adaround_step_f32")
     _count()
 
 
-def recon_act(o, relu, quant=None, prob=1.0, seed=0, out=None):
+def recon_act(o, relu, quant=None, prob=1.0, seed=0, out=None, seed_dev=None):
     """K6 epilogue forward. quant: None or (scale, qmin, qmax) per-tensor."""
     y = torch.empty_like(o) if out is None else out
     s, lo, hi = quant if quant else (1.0, 0.0, 0.0)
     check(lib().dpl_recon_act_f32(o.data_ptr(), y.data_ptr(), o.numel(), int(bool(relu)),
                                   int(quant is not None), float(s), float(lo), float(hi), float(prob),
-                                  int(seed) & (2 ** 64 - 1), _stream()), "dpl_recon_act_f32")
+                                  int(seed) & (2 ** 64 - 1), _lib._ptr(seed_dev), _stream()), "dpl_recon_act_f32")
     _count()
     return y
 
 
-def recon_act_bwd(o, gy, relu, quant=None, prob=1.0, seed=0, out=None):
+def recon_act_bwd(o, gy, relu, quant=None, prob=1.0, seed=0, out=None, seed_dev=None):
     go = torch.empty_like(o) if out is None else out
     s, lo, hi = quant if quant else (1.0, 0.0, 0.0)
     check(lib().dpl_recon_act_bwd_f32(o.data_ptr(), gy.data_ptr(), go.data_ptr(), o.numel(),
                                       int(bool(relu)), int(quant is not None), float(s), float(lo),
-                                      float(hi), float(prob), int(seed) & (2 ** 64 - 1), _stream()),
+                                      float(hi), float(prob), int(seed) & (2 ** 64 - 1), _lib._ptr(seed_dev),
+                                      _stream()),
           "dpl_recon_act_bwd_f32")
     _count()
     return go
 
 
-def recon_loss(o, tgt, inv_count, loss_acc, relu, quant=None, prob=1.0, seed=0, out=None):
+def recon_loss(o, tgt, inv_count, loss_acc, relu, quant=None, prob=1.0, seed=0, out=None, seed_dev=None):
     """Accumulates the L2 loss into loss_acc (float64[1]) and returns dL/do."""
     go = torch.empty_like(o) if out is None else out
     s, lo, hi = quant if quant else (1.0, 0.0, 0.0)
     check(lib().dpl_recon_loss_f32(o.data_ptr(), tgt.data_ptr(), go.data_ptr(), o.numel(),
                                    int(bool(relu)), int(quant is not None), float(s), float(lo),
                                    float(hi), float(prob), int(seed) & (2 ** 64 - 1),
-                                   float(inv_count), _lib._ptr(loss_acc), _stream()),
+                                   float(inv_count), _lib._ptr(loss_acc), _lib._ptr(seed_dev), _stream()),
           "dpl_recon_loss_f32")
     _count()
     return go
@@ -371,3 +372,15 @@ def linear_dgrad(go, w):
     in_f = w.shape[1]
     dx = torch.empty((nrow, in_f), dtype=torch.float32, device=go.device)
     return gemm_tf32(go, 0, out_f, 0, w, 1, in_f, 0, dx, in_f, 0, nrow, in_f, out_f, batch=1)
+
+
+def recon_schedule(d_iter, d_sched, d_seeds, t_max, seed_base=0, rel_start=0.2, start_b=20.0, end_b=2.0,
+                   b1=0.9, b2=0.999):
+    """Device-side per-iteration scalars (beta, Adam bias corrections, mask seeds); increments
+    d_iter. d_iter: int32[1], d_sched: float32[>=3], d_seeds: int64[n] (uint64 bit patterns)."""
+    n = 0 if d_seeds is None else d_seeds.numel()
+    check(lib().dpl_recon_schedule(d_iter.data_ptr(), d_sched.data_ptr(), _lib._ptr(d_seeds), n,
+                                   float(t_max), float(rel_start), float(start_b), float(end_b),
+                                   float(b1), float(b2), int(seed_base) & (2 ** 64 - 1), _stream()),
+          "dpl_recon_schedule")
+    _count()

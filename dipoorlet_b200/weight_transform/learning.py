@@ -45,49 +45,106 @@ def learning_round_mask(layers, q_in, tgt, reg, batch_size, max_epoch, fp_in=Non
             os.environ["DPL_TCGEN05"] = saved[2]
 
 
+def _iteration(layers, x, t, reg_alpha, world, loss_acc, sched, seeds):
+    """One optimisation step on the mini-batch (x, t). Every per-iteration scalar (beta, Adam bias
+    corrections, mask seeds) is read from device memory (`sched`, `seeds`, filled by the
+    schedule kernel), so the same launch sequence serves every iteration — eagerly or as a
+    replayed CUDA graph."""
+    last = len(layers) - 1
+    acts, outs, cfgs = [x], [], []
+    for li, layer in enumerate(layers):
+        w = layer.quant_weight(soft=True)
+        o = layer.dense_forward(acts[-1], w)
+        outs.append(o)
+        cfg = layer.act_cfg(0)
+        cfg["seed_dev"] = seeds[li:li + 1]
+        cfgs.append(cfg)
+        if li < last:
+            acts.append(K.recon_act(o, **cfg))
+    o = outs[-1]
+    loss_acc.zero_()
+    inv_count = float(o.shape[1]) / float(o.numel())     # sum over channels, mean over the rest
+    go = K.recon_loss(o, t, inv_count, loss_acc, **cfgs[-1])
+    for li in range(last, -1, -1):
+        layer = layers[li]
+        gx, gw = layer.dense_backward(acts[li], layer.w_soft, go, need_dx=li > 0)
+        if world > 1:
+            torch.distributed.all_reduce(gw)   # SUM; the 1/world is folded into the step
+        K.adaround_step(gw, layer.wfloor, layer.scale, layer.q_min, layer.q_max, 0.0, layer.round_mask,
+                        layer.m, layer.v, 1, reg_alpha=reg_alpha, grad_scale=1.0 / world, sched=sched)
+        if li > 0:
+            go = K.recon_act_bwd(outs[li - 1], gx, **cfgs[li - 1])
+
+
 def _learn(layers, q_in, tgt, reg, batch_size, max_epoch, fp_in, drop, log_every, head, seed):
     n = q_in.shape[0]
     n_batches = int(np.ceil(n / batch_size))
     world = dist_helper.get_world_size()
     rank0 = dist_helper.get_rank() == 0
-    loss_acc = torch.zeros(1, dtype=torch.float64, device=q_in.device)
+    dev = q_in.device
+    loss_acc = torch.zeros(1, dtype=torch.float64, device=dev)
+    d_iter = torch.zeros(1, dtype=torch.int32, device=dev)
+    sched = torch.zeros(4, dtype=torch.float32, device=dev)
+    seeds = torch.zeros(len(layers) + 1, dtype=torch.int64, device=dev)
+    t_max = float(reg.temp_anneal.t_max)
     ratio = 0.5 if drop else 1.0
-    cur_iter = 0
-    last = len(layers) - 1
+    x_all = q_in if ratio >= 1.0 else torch.empty_like(q_in)
+
+    def schedule():
+        K.recon_schedule(d_iter, sched, seeds, t_max, seed_base=seed)
+
+    # ---- CUDA graph of one full-size iteration: static input buffers + replay ------------------
+    # The launch-bound inner loop (a dozen launches per iteration, millions of iterations at the
+    # default --ada_epoch 5000) is captured once per layer/block and replayed. Multi-rank runs
+    # and DPL_CUDA_GRAPH=0 keep the eager sequence.
+    use_graph = (os.environ.get("DPL_CUDA_GRAPH", "1") != "0" and world == 1 and n >= batch_size
+                 and max_epoch * n_batches >= 8)
+    graph = None
+    if use_graph:
+        xb = torch.empty_like(x_all[:batch_size])
+        tb = torch.empty_like(tgt[:batch_size])
+        state = [(l.round_mask.clone(), l.m.clone(), l.v.clone()) for l in layers]
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):       # warm-up outside capture (cuDNN plans, tensor maps)
+                xb.copy_(q_in[:batch_size])
+                tb.copy_(tgt[:batch_size])
+                for _ in range(2):
+                    schedule()
+                    _iteration(layers, xb, tb, reg.alpha, world, loss_acc, sched, seeds)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                schedule()
+                _iteration(layers, xb, tb, reg.alpha, world, loss_acc, sched, seeds)
+        except Exception as e:   # capture not possible (e.g. an op that syncs): stay eager
+            logger.warning("CUDA graph capture of the rounding loop failed (%s); running eagerly" % (e,))
+            graph = None
+        # the warm-up / capture iterations must not count: restore alpha, Adam state and t
+        for l, (a, m, v) in zip(layers, state):
+            l.round_mask.copy_(a)
+            l.m.copy_(m)
+            l.v.copy_(v)
+        d_iter.zero_()
+
     for epoch in range(max_epoch):
-        x_all = q_in
         if ratio < 1.0:  # QDrop: a fresh Bernoulli mix of quantised and fp block inputs per epoch
-            x_all = K.mix_drop(q_in, fp_in, ratio, _seed(seed, epoch, 991))
+            K.mix_drop(q_in, fp_in, ratio, _seed(seed, epoch, 991), out=x_all)
         for idx in range(n_batches):
             st, ed = idx * batch_size, min((idx + 1) * batch_size, n)
-            beta = reg.update(cur_iter)
-            acts, outs, cfgs = [x_all[st:ed]], [], []
-            for li, layer in enumerate(layers):
-                w = layer.quant_weight(soft=True)
-                o = layer.dense_forward(acts[-1], w)
-                outs.append(o)
-                cfgs.append(layer.act_cfg(_seed(seed, cur_iter, li)))
-                if li < last:
-                    acts.append(K.recon_act(o, **cfgs[-1]))
-            o = outs[-1]
-            loss_acc.zero_()
-            inv_count = float(o.shape[1]) / float(o.numel())     # sum over channels, mean over the rest
-            go = K.recon_loss(o, tgt[st:ed], inv_count, loss_acc, **cfgs[-1])
-            for li in range(last, -1, -1):
-                layer = layers[li]
-                gx, gw = layer.dense_backward(acts[li], layer.w_soft, go, need_dx=li > 0)
-                if world > 1:
-                    torch.distributed.all_reduce(gw)   # SUM; the 1/world is folded into the step
-                K.adaround_step(gw, layer.wfloor, layer.scale, layer.q_min, layer.q_max, beta,
-                                layer.round_mask, layer.m, layer.v, cur_iter + 1, reg_alpha=reg.alpha,
-                                grad_scale=1.0 / world)
-                if li > 0:
-                    go = K.recon_act_bwd(outs[li - 1], gx, **cfgs[li - 1])
-            cur_iter += 1
+            if graph is not None and ed - st == batch_size:
+                xb.copy_(x_all[st:ed])
+                tb.copy_(tgt[st:ed])
+                graph.replay()
+            else:
+                schedule()
+                _iteration(layers, x_all[st:ed], tgt[st:ed], reg.alpha, world, loss_acc, sched, seeds)
         if epoch % log_every == 0 and rank0:
             logger.info("Epoch: {:<5} L2 Loss: {:>10.3f} Beta: {:>3.3f}".format(
-                epoch, float(loss_acc.item()), reg.beta))
+                epoch, float(loss_acc.item()), float(sched[0].item())))
     loss = float(loss_acc.item()) if max_epoch > 0 else float("nan")
+    reg.beta = float(sched[0].item()) if max_epoch > 0 else reg.beta
     if rank0:
         for layer in layers:
             h = reg.rectified_sigmoid(layer.round_mask)

@@ -155,12 +155,14 @@ int dpl_adaround_weight_f32(const float* d_wfloor, const float* d_alpha, const f
 /* One fused optimiser step on alpha given dL/dW_soft:
  *   g = dW * s * h'(alpha) * [not clamped] + d/dalpha( reg_alpha * sum(1 - |2h-1|^beta) )
  *   Adam(lr, b1, b2, eps, step) in place on (alpha, m, v).
- * Also accumulates the regulariser value into d_reg (float64[1]) when non-NULL. */
+ * Also accumulates the regulariser value into d_reg (float64[1]) when non-NULL.
+ * d_sched (optional, float32[3] = {beta, 1-b1^t, sqrt(1-b2^t)} written by dpl_recon_schedule)
+ * overrides beta / step so that a captured CUDA graph can be replayed every iteration. */
 int dpl_adaround_step_f32(const float* d_grad_w, const float* d_wfloor, const float* d_scale,
                           int n_channels, uint64_t inner, float qmin, float qmax, float beta,
                           float reg_alpha, float lr, float b1, float b2, float eps, int step,
                           float grad_scale, float* d_alpha, float* d_m, float* d_v,
-                          double* d_reg, void* stream);
+                          double* d_reg, const float* d_sched, void* stream);
 
 /* K6 epilogues — layer activation of the reconstruction loop: y = [drop-]fakequant(relu(o))
  * (AdaQLayer.forward tail, weight_transform/ada_quant_layer.py:245-251; quant_acti :28-36),
@@ -169,13 +171,23 @@ int dpl_adaround_step_f32(const float* d_grad_w, const float* d_wfloor, const fl
  * rest => inv_count = channels / numel), and the QDrop block input
  * where(u < prob, q_in, fp_in) (brecq.py:169-170). Masks are regenerated from (seed, index). */
 int dpl_recon_act_f32(const float* d_o, float* d_y, uint64_t n, int relu, int quant, float scale,
-                      float qmin, float qmax, float prob, uint64_t seed, void* stream);
+                      float qmin, float qmax, float prob, uint64_t seed,
+                      const unsigned long long* d_seed, void* stream);
 int dpl_recon_act_bwd_f32(const float* d_o, const float* d_gy, float* d_go, uint64_t n, int relu,
                           int quant, float scale, float qmin, float qmax, float prob,
-                          uint64_t seed, void* stream);
+                          uint64_t seed, const unsigned long long* d_seed, void* stream);
 int dpl_recon_loss_f32(const float* d_o, const float* d_tgt, float* d_go, uint64_t n, int relu,
                        int quant, float scale, float qmin, float qmax, float prob, uint64_t seed,
-                       float inv_count, double* d_loss, void* stream);
+                       float inv_count, double* d_loss, const unsigned long long* d_seed,
+                       void* stream);
+/* (d_seed, optional: the mask seed is read from device memory instead of `seed`.)
+ * dpl_recon_schedule: one-thread kernel computing the scalars of iteration t = *d_iter — the
+ * regulariser temperature beta(t) (TempDecay, ada_quant_layer.py:117-130), Adam's bias
+ * corrections and one mask seed per layer — then t += 1. With it a whole iteration of the
+ * reconstruction loop is a replayable CUDA graph. */
+int dpl_recon_schedule(int* d_iter, float* d_sched, unsigned long long* d_seeds, int n_seeds,
+                       double t_max, double rel_start, double start_b, double end_b, double b1,
+                       double b2, uint64_t seed_base, void* stream);
 int dpl_mix_drop_f32(const float* d_a, const float* d_b, float* d_y, uint64_t n, float prob,
                      uint64_t seed, void* stream);
 

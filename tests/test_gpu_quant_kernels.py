@@ -148,3 +148,33 @@ def test_learning_loop_matches_torch_autograd(dpl_built, relu, drop, monkeypatch
         assert interior.float().mean().item() > 0.8
         same = ((ref.round_mask.detach() >= 0) == (got.round_mask >= 0))[interior].float().mean().item()
         assert same > 0.999
+
+
+def test_cuda_graph_replay_equals_eager(dpl_built, monkeypatch):
+    """The captured-and-replayed iteration (DPL_CUDA_GRAPH=1) must produce the same alpha as the
+    eager launch sequence, including a ragged last mini-batch that runs eagerly in both."""
+    import torch
+    from dipoorlet_b200 import onnx_lite as ol
+    from dipoorlet_b200.weight_transform.ada_quant_layer import AdaQLayer, adaround_reg
+    from dipoorlet_b200.weight_transform.learning import learning_round_mask
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(7)
+    n, bs, epochs = 20, 8, 10          # batches of 8, 8, 4
+    x_fp = torch.randn((n, 8, 12, 12), device=dev, generator=g)
+    x = torch.round(x_fp / 0.05) * 0.05
+    w = torch.randn((16, 8, 3, 3), device=dev, generator=g) * 0.2
+    b = torch.randn(16, device=dev, generator=g) * 0.1
+    attrs = {"dilations": [1, 1], "group": 1, "kernel_shape": [3, 3], "pads": [1, 1, 1, 1], "strides": [1, 1]}
+    with torch.no_grad():
+        tgt = torch.relu(torch.nn.functional.conv2d(x_fp, w, b, padding=1))
+    scale = (w.abs().amax(dim=(1, 2, 3)) / 127).contiguous()
+    res = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DPL_CUDA_GRAPH", mode)
+        layer = AdaQLayer(ol.Node("Conv", ["x", "w"], ["y"], "c", attrs), w, b, scale, -127, 127, True, device=dev)
+        reg = adaround_reg(epochs * 3)
+        learning_round_mask([layer], x, tgt, reg, bs, epochs, seed=3)
+        res.append(layer.round_mask.clone())
+    assert torch.allclose(res[0], res[1], rtol=0, atol=1e-6), (res[0] - res[1]).abs().max().item()
+    assert (res[0] - AdaQLayer(ol.Node("Conv", ["x", "w"], ["y"], "c", attrs), w, b, scale, -127, 127, True,
+                               device=dev).round_mask).abs().max().item() > 1e-3   # it did learn

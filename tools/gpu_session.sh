@@ -20,7 +20,7 @@ for s in $STEPS; do
                  python tools/kbench.py --batch 16 --quick > gpurun_out/ncu_run.log 2>&1; tail -3 gpurun_out/ncu_run.log ;;
     configs) timeout 1200 python tools/run_configs.py --configs ${CONFIGS:-2 3 4 5} --ada-epoch ${ADA_EPOCH:-10} > gpurun_out/configs.log 2>&1; tail -8 gpurun_out/configs.log ;;
     benchcb) DPL_CUDNN_BENCHMARK=1 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cudnn_benchmark.json 2> gpurun_out/bench_cb.err; tail -c 1500 gpurun_out/bench_cudnn_benchmark.json; tail -3 gpurun_out/bench_cb.err ;;
-    batch)   for b in 16 64; do timeout 600 python bench.py --steps 2 --warmup 3 --batch $b --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('batch', d['config']['forward_batch'], 'value', round(d['value']), 'e2e', round(d['e2e']['value']), 'hist frac', round(d['roofline']['frac'],3))"; done ;;
+    batch)   for b in ${BATCHES:-32 128}; do timeout 600 python bench.py --steps 2 --warmup 3 --batch $b --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('batch', d['config']['forward_batch'], 'value', round(d['value']), 'e2e', round(d['e2e']['value']), 'hist frac', round(d['roofline']['frac'],3))"; done ;;
     ncuhist) timeout 600 ncu --set full --clock-control none --import-source on -k regex:'hist_lc3|segstats_tiles' -c 2 -f -o gpurun_out/prof_hist_b32 \
                  python tools/kbench.py --batch 32 --quick > gpurun_out/ncu_hist_run.log 2>&1; tail -2 gpurun_out/ncu_hist_run.log ;;
     smoke)   timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3 ;;
