@@ -96,9 +96,9 @@ def _learn(layers, q_in, tgt, reg, batch_size, max_epoch, fp_in, drop, log_every
     # ---- CUDA graph of one full-size iteration: static input buffers + replay ------------------
     # The launch-bound inner loop (a dozen launches per iteration, millions of iterations at the
     # default --ada_epoch 5000) is captured once per layer/block and replayed. Multi-rank runs
-    # and DPL_CUDA_GRAPH=0 keep the eager sequence.
+    # and DPL_CUDA_GRAPH=0 keep the eager sequence, as do short runs (capture costs ~50 iterations).
     use_graph = (os.environ.get("DPL_CUDA_GRAPH", "1") != "0" and world == 1 and n >= batch_size
-                 and max_epoch * n_batches >= 8)
+                 and max_epoch * n_batches >= int(os.environ.get("DPL_CUDA_GRAPH_MIN_ITERS", "256")))
     graph = None
     if use_graph:
         xb = torch.empty_like(x_all[:batch_size])

@@ -96,6 +96,7 @@ def test_learning_loop_matches_torch_autograd(dpl_built, relu, drop, monkeypatch
     from dipoorlet_b200.weight_transform.learning import learning_round_mask
     from oracle import adaround as OA
     monkeypatch.setenv("DPL_RECON_TF32", "0")   # fp32 vs fp32: this test is about the update rule
+    monkeypatch.setenv("DPL_CUDA_GRAPH_MIN_ITERS", "8")   # exercise the captured path
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     dev = torch.device("cuda")
@@ -169,6 +170,7 @@ def test_cuda_graph_replay_equals_eager(dpl_built, monkeypatch):
         tgt = torch.relu(torch.nn.functional.conv2d(x_fp, w, b, padding=1))
     scale = (w.abs().amax(dim=(1, 2, 3)) / 127).contiguous()
     res = []
+    monkeypatch.setenv("DPL_CUDA_GRAPH_MIN_ITERS", "8")
     for mode in ("0", "1"):
         monkeypatch.setenv("DPL_CUDA_GRAPH", mode)
         layer = AdaQLayer(ol.Node("Conv", ["x", "w"], ["y"], "c", attrs), w, b, scale, -127, 127, True, device=dev)
