@@ -6,9 +6,11 @@ Replaces the reference's per-sample `ort.InferenceSession.run` with every node o
 promoted to a graph output and copied back to the host (dipoorlet/forward_net.py:195-216)
 and the per-node sessions of ActivationCache.forward_subnet (forward_net.py:81-128).
 
-STAND-IN NOTICE: the dense operators (Conv / Gemm / pooling)
-are issued through torch's CUDA ops (cuDNN / cuBLAS, true fp32: TF32 disabled), i.e. a
-library call playing the role onnxruntime's CUDA EP plays in the reference. The statistics,
+1x1 convolutions and Gemm layers run on libdpl_b200's tcgen05 GEMM in 3xTF32 mode (fp32-accurate
+products on the TF32 tensor cores, dpl_gemm_tf32x3). STAND-IN NOTICE (SURVEY.md §7 step 5,
+§8 f2): the remaining dense operators (k x k / strided / depthwise convolutions, pooling) are
+still issued through torch's CUDA ops (cuDNN, true fp32: TF32 disabled), i.e. a library call
+playing the role onnxruntime's CUDA EP plays in the reference. The statistics,
 fake-quant and rounding kernels — the hot path this repo is about — are libdpl_b200.so.
 QuantizeLinear + DequantizeLinear pairs are executed as ONE fused K5 launch.
 """
@@ -41,6 +43,9 @@ class Engine:
         self.allow_tf32 = allow_tf32
         self.params = {}
         self.zero_points = {}
+        self._w_lo = {}            # tf32 residuals of the 1x1 / Gemm weights (3xTF32 operand)
+        self._tc_off = set()       # nodes the tensor-core tile could not address
+        self.tensor_cores = os.environ.get("DPL_ENGINE_TCGEN05", "1") != "0"
         self.refresh_initializers()
         self.nodes = list(onnx_graph.model.graph.nodes)
         self._fused_q = set()
@@ -49,6 +54,7 @@ class Engine:
         """(Re)upload initializers — after bias correction / rounding rewrote weights."""
         inits = self.g.model.graph.initializers
         for name in (names if names is not None else inits):
+            self._w_lo.pop(name, None)
             arr = inits[name]
             if arr.dtype == np.float64:
                 arr = arr.astype(np.float32)
@@ -137,6 +143,20 @@ class Engine:
             return env[name]
         return self.params[name]
 
+    def _tc_conv_ok(self, node, x, w, stride, dil, lo, hi):
+        """1x1, stride 1, unpadded, ungrouped convolutions whose C_in and H*W are multiples of 4
+        (TMA's 16-byte rule) run on libdpl_b200's 3xTF32 tensor-core GEMM."""
+        return (self.tensor_cores and x.is_cuda and node.name not in self._tc_off and w.dim() == 4
+                and list(w.shape[2:]) == [1, 1] and list(stride) == [1, 1] and list(dil) == [1, 1]
+                and not any(lo) and not any(hi) and node.attrs.get("group", 1) == 1
+                and x.is_contiguous() and x.shape[1] % 4 == 0 and (x.shape[2] * x.shape[3]) % 4 == 0)
+
+    def _residual(self, name, w2):
+        lo = self._w_lo.get(name)
+        if lo is None or lo.shape != w2.shape:
+            lo = self._w_lo[name] = K.tf32_residual(w2.contiguous())
+        return lo
+
     def _host(self, name, env):
         """Small constant operands (Clip bounds, Reshape targets) read on the host without
         a device sync when they are initializers."""
@@ -153,6 +173,12 @@ class Engine:
             stride = a.get("strides", [1] * nd)
             dil = a.get("dilations", [1] * nd)
             sym, lo, hi = _sym_pads(a.get("pads", [0] * (2 * nd)), nd)
+            if self._tc_conv_ok(node, x, w, stride, dil, lo, hi):
+                try:    # 1x1 convolution as a 3xTF32 GEMM on the tcgen05 tile (fp32-accurate)
+                    w2 = w.view(w.shape[0], w.shape[1])
+                    return [K.conv1x1_forward_x3(x, w2, self._residual(node.input[1], w2), b)]
+                except K.GemmUnsupported:
+                    self._tc_off.add(node.name)
             if not sym:
                 x = F.pad(x, [p for i in reversed(range(nd)) for p in (lo[i], hi[i])])
                 lo = [0] * nd
@@ -206,6 +232,12 @@ class Engine:
             if a.get("transA", 0):
                 x = x.t()
             if alpha == 1.0 and beta == 1.0 and a.get("transB", 0) and (c is None or c.dim() == 1):
+                if (self.tensor_cores and x.is_cuda and node.name not in self._tc_off and x.dim() == 2
+                        and x.shape[1] % 4 == 0 and x.is_contiguous()):
+                    try:
+                        return [K.linear_forward_x3(x, w, None, c)]
+                    except K.GemmUnsupported:
+                        self._tc_off.add(node.name)
                 return [F.linear(x, w, c)]
             y = alpha * (x @ (w.t() if a.get("transB", 0) else w))
             return [y if c is None else y + beta * c]

@@ -384,3 +384,49 @@ def recon_schedule(d_iter, d_sched, d_seeds, t_max, seed_base=0, rel_start=0.2, 
                                    float(b1), float(b2), int(seed_base) & (2 ** 64 - 1), _stream()),
           "dpl_recon_schedule")
     _count()
+
+
+def tf32_residual(x):
+    """x - trunc_tf32(x): the low operand of the 3xTF32 product (weights: computed once)."""
+    lo = torch.empty_like(x)
+    check(lib().dpl_tf32_residual_f32(x.data_ptr(), lo.data_ptr(), x.numel(), _stream()),
+          "dpl_tf32_residual_f32")
+    _count()
+    return lo
+
+
+def gemm_tf32x3(a, a_lo, a_major, lda, a_batch_stride, b, b_major, ldb, b_batch_stride, d, ldd,
+                d_batch_stride, M, N, K, batch=1, bias=None, bias_mode=0, relu=False):
+    dev = d.device
+    flag = _gemm_err.get(dev)
+    if flag is None:
+        flag = _gemm_err[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = lib().dpl_gemm_tf32x3(a.data_ptr(), a_lo.data_ptr(), int(a_major), int(lda), int(a_batch_stride),
+                               b.data_ptr(), int(b_major), int(ldb), int(b_batch_stride), d.data_ptr(),
+                               int(ldd), int(d_batch_stride), int(M), int(N), int(K), int(batch),
+                               _lib._ptr(bias), int(bias_mode), int(bool(relu)), flag.data_ptr(), _stream())
+    if st == 10003:
+        raise GemmUnsupported(lib().dpl_last_error().decode("utf-8", "replace"))
+    check(st, "dpl_gemm_tf32x3")
+    _count()
+    return d
+
+
+def conv1x1_forward_x3(x, w, w_lo, bias=None, relu=False, out=None):
+    """fp32-accurate O[img][co][hw] = W[co][ci] x X[img][ci][hw] (+ bias[co]) on tensor cores."""
+    n, ci, hh, ww = x.shape
+    co = w.shape[0]
+    hw = hh * ww
+    o = torch.empty((n, co, hh, ww), dtype=torch.float32, device=x.device) if out is None else out
+    return gemm_tf32x3(w, w_lo, 0, ci, 0, x, 1, hw, ci * hw, o, hw, co * hw, co, hw, ci, batch=n,
+                       bias=bias, bias_mode=1 if bias is not None else 0, relu=relu)
+
+
+def linear_forward_x3(x, w, w_lo=None, bias=None):
+    """fp32-accurate Y = X W^T (+ bias): A = X (its residual is computed here, X is small),
+    B = W is split inside the kernel, so `w_lo` is not needed."""
+    nrow, k = x.shape
+    out_f = w.shape[0]
+    y = torch.empty((nrow, out_f), dtype=torch.float32, device=x.device)
+    return gemm_tf32x3(x, tf32_residual(x), 0, k, 0, w, 0, k, 0, y, out_f, 0, nrow, out_f, k, batch=1,
+                       bias=bias, bias_mode=2 if bias is not None else 0)

@@ -97,7 +97,12 @@ def _learn(layers, q_in, tgt, reg, batch_size, max_epoch, fp_in, drop, log_every
     # The launch-bound inner loop (a dozen launches per iteration, millions of iterations at the
     # default --ada_epoch 5000) is captured once per layer/block and replayed. Multi-rank runs
     # and DPL_CUDA_GRAPH=0 keep the eager sequence, as do short runs (capture costs ~50 iterations).
-    use_graph = (os.environ.get("DPL_CUDA_GRAPH", "1") != "0" and world == 1 and n >= batch_size
+    # Measured (tools/learn_bench.py): iterations on 56x56 feature maps are GPU bound (0.2-1.2 ms
+    # each) and gain nothing from replay — the static-input copies even cost — so "auto" only
+    # captures when a mini-batch of block inputs is small (launch-bound regime); "1" forces it.
+    mode = os.environ.get("DPL_CUDA_GRAPH", "auto")
+    small = q_in[:batch_size].numel() * 4 <= (4 << 20)
+    use_graph = ((mode == "1" or (mode == "auto" and small)) and world == 1 and n >= batch_size
                  and max_epoch * n_batches >= int(os.environ.get("DPL_CUDA_GRAPH_MIN_ITERS", "256")))
     graph = None
     if use_graph:

@@ -212,6 +212,18 @@ int dpl_gemm_tf32(const float* d_a, int a_major, long long lda, long long a_batc
                   int batch, int fold_batch, int split_k, const float* d_bias, int bias_mode,
                   int relu, int* d_error_flag, void* stream);
 
+/* 3xTF32 variant: fp32-accurate products on the TF32 tensor cores,
+ *   a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo   (x_hi = top 19 bits, x_lo = x - x_hi),
+ * for the calibration forward (activations must stay within fp32 rounding of the reference's
+ * fp32 ORT path, dipoorlet/forward_net.py:200-216). d_a_lo = dpl_tf32_residual_f32(d_a) is
+ * computed once per weight; the residual of B is formed in shared memory inside the kernel. */
+int dpl_tf32_residual_f32(const float* d_x, float* d_lo, uint64_t n, void* stream);
+int dpl_gemm_tf32x3(const float* d_a, const float* d_a_lo, int a_major, long long lda,
+                    long long a_batch_stride, const float* d_b, int b_major, long long ldb,
+                    long long b_batch_stride, float* d_d, long long ldd, long long d_batch_stride,
+                    int M, int N, int K, int batch, const float* d_bias, int bias_mode, int relu,
+                    int* d_error_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

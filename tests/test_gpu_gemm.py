@@ -73,3 +73,41 @@ def test_unsupported_alignment_is_reported(dpl_built):
     w = torch.randn((16, 8), device="cuda")
     with pytest.raises(K.GemmUnsupported):
         K.conv1x1_forward(x, w)
+
+
+@pytest.mark.parametrize("dims", [(3, 64, 256, 56), (2, 96, 40, 28), (4, 1024, 256, 14), (1, 8, 136, 12)])
+def test_conv1x1_forward_3xtf32_is_fp32_accurate(dpl_built, dims):
+    """3xTF32 must sit at fp32 accuracy (the calibration forward is compared at 1e-5):
+    error vs float64 no worse than ~2x the error of a plain fp32 convolution."""
+    import torch
+    import torch.nn.functional as F
+    from dipoorlet_b200 import kernels as K
+    n, ci, co, hw = dims
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn((n, ci, hw, hw), device="cuda", generator=g)
+    w = torch.randn((co, ci), device="cuda", generator=g) * 0.1
+    b = torch.randn(co, device="cuda", generator=g)
+    o = K.conv1x1_forward_x3(x, w, K.tf32_residual(w), b)
+    K.gemm_check_errors()
+    want = torch.einsum("oc,nchw->nohw", w.double(), x.double()) + b.double().view(1, -1, 1, 1)
+    torch.backends.cudnn.allow_tf32 = False
+    ref32 = F.conv2d(x, w.view(co, ci, 1, 1), b)
+    err = (o.double() - want).abs().max().item()
+    err32 = (ref32.double() - want).abs().max().item()
+    scale = want.abs().max().item()
+    assert err <= max(3 * err32, 2e-6 * scale), (err, err32, scale)
+    assert err <= 1e-5 * scale
+
+
+def test_linear_forward_3xtf32(dpl_built):
+    import torch
+    from dipoorlet_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn((64, 2048), device="cuda", generator=g)
+    w = torch.randn((1000, 2048), device="cuda", generator=g) * 0.02
+    b = torch.randn(1000, device="cuda", generator=g)
+    y = K.linear_forward_x3(x, w, K.tf32_residual(w), b)
+    K.gemm_check_errors()
+    want = x.double() @ w.double().t() + b.double()
+    err = (y.double() - want).abs().max().item()
+    assert err <= 1e-5 * want.abs().max().item(), err
