@@ -291,7 +291,10 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "images_per_gpu": n_img, "forward_batch": args.batch,
                    "l2": "inputs larger than L2: every timed kernel streams a %.1f GB batch of blobs "
                          "(126 MB L2)" % (4 * elems_per_img * args.batch / 1e9),
-                   "forward": "torch/cuDNN fp32 (TF32 off) stand-in producer; statistics = libdpl_b200.so",
+                   "forward": ("1x1 conv / Gemm: libdpl_b200 tcgen05 3xTF32 GEMM (fp32-accurate); k x k, strided convs and pooling: "
+                               "torch/cuDNN fp32 stand-in (TF32 off)") if os.environ.get("DPL_ENGINE_TCGEN05", "1") != "0"
+                   else "torch/cuDNN fp32 (TF32 off) stand-in producer",
+                   "statistics": "libdpl_b200.so (K1 segstats, K2 histogram variant 7, K3 percentile)",
                    "resident_blobs": bool(resident_used["v"])},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_per_step,
@@ -307,7 +310,10 @@ def run_ours(args):
                      "traffic_source": "ncu capture at batch 32, scaled by bytes per launch",
                      "launches_timed": len(hist_ms),
                      "bytes_per_launch": float(np.mean(hist_bytes)) if hist_bytes else 0,
-                     "ms_per_launch": float(np.mean(hist_ms)) if hist_ms else None},
+                     "ms_per_launch": float(np.mean(hist_ms)) if hist_ms else None,
+                     "ms_per_launch_median": float(np.median(hist_ms)) if hist_ms else None,
+                     "ms_per_launch_min": float(np.min(hist_ms)) if hist_ms else None,
+                     "ms_per_launch_max": float(np.max(hist_ms)) if hist_ms else None},
     }
     if not args.no_cpu_baseline and world == 1:
         try:
