@@ -134,6 +134,7 @@ class CalibrationSession:
         self.ws = K.Workspace(dev)
         self.in_shapes = {n: _per_image_shape(onnx_graph, n) for n in onnx_graph.network_inputs}
         self.h2d_bytes = 0
+        self._copy_stream = None
         f32 = dict(dtype=torch.float32, device=dev)
         self.blob_min = torch.full((self.n_stats,), float("inf"), **f32)
         self.blob_max = torch.full((self.n_stats,), float("-inf"), **f32)
@@ -156,14 +157,47 @@ class CalibrationSession:
         reusable = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
         return per_img * (self.n_local + 2 * self.batch_size) < 0.85 * (free + reusable)
 
+    def _ranges(self):
+        return [(b0, min(b0 + self.batch_size, self.ed)) for b0 in range(self.st, self.ed, self.batch_size)]
+
+    def _upload(self, b0, b1):
+        feeds = {}
+        for name, shape in self.in_shapes.items():
+            host = self.source.fetch(name, b0, b1, shape)
+            self.h2d_bytes += host.numel() * 4
+            feeds[name] = host.to(self.device, non_blocking=True)
+        return feeds
+
     def batches(self):
-        for b0 in range(self.st, self.ed, self.batch_size):
-            b1 = min(b0 + self.batch_size, self.ed)
-            feeds = {}
-            for name, shape in self.in_shapes.items():
-                host = self.source.fetch(name, b0, b1, shape)
-                self.h2d_bytes += host.numel() * 4
-                feeds[name] = host.to(self.device, non_blocking=True)
+        """Forward batches with the NEXT batch's host->device copy issued on a side stream
+        while the current batch computes (the images come from pinned host memory)."""
+        ranges = self._ranges()
+        if self.device.type != "cuda" or not ranges:
+            for b0, b1 in ranges:
+                blobs = self.engine.run(self._upload(b0, b1), want="all")
+                yield b0 - self.st, b1 - self.st, K.BlobBatch([blobs[n] for n in self.names])
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        copy = self._copy_stream
+
+        def prefetch(rng):
+            copy.wait_stream(main)          # allocator safety: buffers freed on `main` may be reused
+            with torch.cuda.stream(copy):
+                feeds = self._upload(*rng)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+            return feeds, ev
+
+        nxt = prefetch(ranges[0])
+        for i, (b0, b1) in enumerate(ranges):
+            feeds, ev = nxt
+            main.wait_event(ev)
+            for t in feeds.values():
+                t.record_stream(main)
+            if i + 1 < len(ranges):
+                nxt = prefetch(ranges[i + 1])
             blobs = self.engine.run(feeds, want="all")
             yield b0 - self.st, b1 - self.st, K.BlobBatch([blobs[n] for n in self.names])
 
