@@ -23,6 +23,7 @@ namespace {
 constexpr int kOctThreads = 512;
 constexpr int kOctWarps = kOctThreads / 32;
 constexpr int kOctCtasPerSm = 2;
+constexpr int kTailCap = 4096;   // survivors that fit in shared memory: one warp finishes alone
 
 struct PassAcc {
   double sum;
@@ -70,6 +71,10 @@ octav_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_t n_segment
              float* __restrict__ out_s, int* __restrict__ out_iters) {
   __shared__ double s_sum[kOctWarps];
   __shared__ unsigned long long s_gt[kOctWarps], s_le[kOctWarps];
+  __shared__ float s_tail[kTailCap];
+  __shared__ uint32_t s_wcnt[kOctWarps];
+  __shared__ float s_tail_s;
+  __shared__ int s_tail_it, s_tail_fallback;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* my_scratch = scratch + (uint64_t)blockIdx.x * scratch_stride;
 
@@ -183,6 +188,67 @@ octav_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_t n_segment
       const float s_next = __fdiv_rn((float)acc.sum, (float)den);
       if (fabsf(s_next - s) < 1e-6f) break;
       s = s_next;
+      // ---- tail phase: the survivors fit in shared memory. The remaining updates only touch a
+      // shrinking handful of elements, where the block-wide reduction (three barriers per
+      // update) would dominate: gather them once and let warp 0 finish with shuffles only.
+      if (acc.gt <= (unsigned long long)kTailCap && it + 1 < max_iter) {
+        __syncwarp();
+        if (lane == 0) s_wcnt[warp] = (uint32_t)cnt;
+        __syncthreads();
+        uint32_t off = 0;
+        for (int w = 0; w < warp; ++w) off += s_wcnt[w];
+        for (uint64_t i = lane; i < cnt; i += 32) s_tail[off + i] = __ldcg(wout + i);
+        __syncthreads();
+        if (warp == 0) {
+          uint32_t m = (uint32_t)acc.gt;
+          float s2 = s, thr2 = thr;
+          int it2 = it + 1;
+          int fallback = 0;
+          const unsigned lt_mask = (1u << lane) - 1u;
+          for (; it2 < max_iter; ++it2) {
+            if (!(s2 >= thr2)) {   // would need elements dropped earlier: hand back to the block
+              fallback = 1;
+              break;
+            }
+            uint32_t wr = 0;
+            float blk = 0.f;
+            for (uint32_t i = 0; i < m; i += 32) {
+              const uint32_t j = i + lane;
+              const float a = (j < m) ? s_tail[j] : 0.f;
+              const bool g = a > s2;
+              const unsigned mg = __ballot_sync(0xffffffffu, g);
+              __syncwarp();
+              if (g) {
+                blk += a;
+                s_tail[wr + __popc(mg & lt_mask)] = a;
+              }
+              wr += __popc(mg);
+              __syncwarp();
+            }
+            const double sum = warp_sum((double)blk);
+            m = wr;
+            thr2 = s2;
+            const double den2 = k_const * (double)(n - m) + (double)m;
+            const float sn = __fdiv_rn((float)sum, (float)den2);
+            if (fabsf(sn - s2) < 1e-6f) break;
+            s2 = sn;
+          }
+          if (lane == 0) {
+            s_tail_s = s2;
+            s_tail_it = it2;
+            s_tail_fallback = fallback;
+          }
+        }
+        __syncthreads();
+        s = s_tail_s;
+        if (s_tail_fallback) {
+          have = false;            // re-stream the segment at the next update
+          it = s_tail_it - 1;      // the for-increment restores it
+          continue;
+        }
+        it = s_tail_it;
+        break;
+      }
     }
     if (threadIdx.x == 0) {
       out_s[sg] = s;
