@@ -180,24 +180,36 @@ class CalibrationSession:
         main = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
+            # two persistent device buffers per input, allocated on the main stream once: side-stream
+            # allocations would live in their own allocator pool and force cudaMalloc / cache flushes
+            # when the resident blobs already fill most of HBM
+            self._in_bufs = [{n: torch.empty((self.batch_size,) + tuple(shp), dtype=torch.float32, device=self.device)
+                              for n, shp in self.in_shapes.items()} for _ in range(2)]
         copy = self._copy_stream
 
-        def prefetch(rng):
-            copy.wait_stream(main)          # allocator safety: buffers freed on `main` may be reused
+        def prefetch(slot, rng):
+            b0, b1 = rng
+            copy.wait_stream(main)          # the buffer's previous reader (two batches back) is done
+            feeds = {}
             with torch.cuda.stream(copy):
-                feeds = self._upload(*rng)
+                for name, shape in self.in_shapes.items():
+                    host = self.source.fetch(name, b0, b1, shape)
+                    self.h2d_bytes += host.numel() * 4
+                    dst = self._in_bufs[slot][name][:b1 - b0]
+                    dst.copy_(host, non_blocking=True)
+                    feeds[name] = dst
             ev = torch.cuda.Event()
             ev.record(copy)
             return feeds, ev
 
-        nxt = prefetch(ranges[0])
+        nxt = prefetch(0, ranges[0])
         for i, (b0, b1) in enumerate(ranges):
             feeds, ev = nxt
             main.wait_event(ev)
-            for t in feeds.values():
-                t.record_stream(main)
+            if self.keep_resident:   # the input blob is kept for pass 2: detach it from the staging buffer
+                feeds = {k: v.clone() for k, v in feeds.items()}
             if i + 1 < len(ranges):
-                nxt = prefetch(ranges[i + 1])
+                nxt = prefetch((i + 1) & 1, ranges[i + 1])
             blobs = self.engine.run(feeds, want="all")
             yield b0 - self.st, b1 - self.st, K.BlobBatch([blobs[n] for n in self.names])
 

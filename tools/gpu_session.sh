@@ -10,7 +10,7 @@ for s in $STEPS; do
   case $s in
     tests)   timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; grep -E 'passed|failed|FAILED|Error' gpurun_out/pytest_gpu.log | tail -30 ;;
     kbench)  timeout 300 python tools/kbench.py --batch 32 > gpurun_out/kbench.log 2>&1; cat gpurun_out/kbench.log | tail -40 ;;
-    bench)   timeout 600 python bench.py --steps 3 --warmup 3 --hist-variant ${HIST_VARIANT:-4} > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err ;;
+    bench)   timeout 600 python bench.py --steps 3 --warmup 3 --hist-variant ${HIST_VARIANT:-0} > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err ;;
     ref)     timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 1500 gpurun_out/bench_ref.json ;;
     launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv \
                  --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --images 64 --no-cpu-baseline \
