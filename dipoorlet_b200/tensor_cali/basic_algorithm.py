@@ -72,21 +72,48 @@ def find_clip_val_octav(onnx_graph, args, **kwargs):
 
 
 def find_clip_val_minmax_weight(onnx_graph, args):
-    """Per-output-channel min / max of every weight-like initializer (host side, a few
-    ms; basic_algorithm.py:72-91)."""
-    tensors, transposed = {}, set()
+    """Per-output-channel min / max of every weight-like initializer (basic_algorithm.py:72-91).
+    On the GPU this is ONE K1 launch over the weights the engine already holds in HBM (a channel
+    is a segment); the host NumPy path remains for ConvTranspose weights (transposed first) and
+    for the CPU unit tests."""
+    names, transposed = [], set()
     for node in onnx_graph.graph.node:
         if node.op_type in LAYER_HAS_WEIGHT:
             for name in node.input[1:]:
-                tensors[name] = onnx_graph.get_initializer(name)
+                if name not in names:
+                    names.append(name)
             if node.op_type == 'ConvTranspose':
                 transposed.add(node.input[1])
+    names = [n for n in names if onnx_graph.get_initializer(n).ndim >= 1]
     out = {}
-    for name, t in tensors.items():
-        if t.ndim < 1:
+    dev = fwd._device_of(args)
+    on_gpu = [n for n in names if n not in transposed and onnx_graph.get_initializer(n).dtype == np.float32
+              and onnx_graph.get_initializer(n).size > 0]
+    import torch
+    if dev.type != "cuda" or not torch.cuda.is_available():
+        on_gpu = []                      # host NumPy, as the reference (weights are a8-small)
+    if on_gpu:
+        from .. import kernels as K
+        eng = fwd._engine_for(onnx_graph, dev)
+        tensors = []
+        for n in on_gpu:
+            t = eng.params[n]
+            tensors.append(t.reshape(t.shape[0], -1) if t.dim() > 1 else t.reshape(-1, 1))
+        batch = K.BlobBatch(tensors)
+        lo = torch.empty(batch.n_segments, dtype=torch.float32, device=dev)
+        hi = torch.empty_like(lo)
+        K.segstats(batch, lo, hi)
+        lo, hi = lo.cpu().numpy(), hi.cpu().numpy()
+        for n, (off, c) in zip(on_gpu, batch.seg_slices()):
+            out[n] = [lo[off:off + c].copy(), hi[off:off + c].copy()]
+    res = {}
+    for n in names:                      # the reference's insertion order
+        if n in out:
+            res[n] = out[n]
             continue
-        if name in transposed:
+        t = onnx_graph.get_initializer(n)
+        if n in transposed:
             t = t.transpose([1, 0, 2, 3])
         flat = t.reshape((t.shape[0], -1))
-        out[name] = [flat.min(-1), flat.max(-1)]
-    return out
+        res[n] = [flat.min(-1), flat.max(-1)]
+    return res

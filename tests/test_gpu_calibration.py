@@ -118,3 +118,23 @@ def test_trt_file_vs_cpu_oracle(setup, algo):
         if algo == "hist":  # the percentile may land one bin away
             tol += 1.5 * float(O.data_max_of(mm[k])) / 2048
         assert abs(got[k] - want[k]) <= tol, (k, got[k], want[k])
+
+
+def test_weight_ranges_on_device_bit_exact(setup):
+    """The per-channel weight min/max (basic_algorithm.py:72-91) come from one K1 launch over
+    the engine's resident weights; they must equal the NumPy per-channel reduction exactly."""
+    from dipoorlet_b200.platform_settings import LAYER_HAS_WEIGHT
+    from dipoorlet_b200.tensor_cali import find_clip_val_minmax_weight
+    from oracle import stats as O
+    graph, args = setup["graph"], setup["args"]
+    got = find_clip_val_minmax_weight(graph, args)
+    weights = {}
+    for node in graph.graph.node:
+        if node.op_type in LAYER_HAS_WEIGHT:
+            for name in node.input[1:]:
+                weights.setdefault(name, graph.get_initializer(name))
+    want = O.weight_minmax(weights)
+    assert list(got) == list(want)
+    for name in want:
+        np.testing.assert_array_equal(got[name][0], np.asarray(want[name][0]))
+        np.testing.assert_array_equal(got[name][1], np.asarray(want[name][1]))
