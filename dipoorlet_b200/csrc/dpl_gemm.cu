@@ -21,6 +21,7 @@
 
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "dpl_common.cuh"
 
@@ -47,6 +48,7 @@ struct GemmParams {
   int bias_mode;        // 0 none, 1 per row (m), 2 per column (n)
   int relu;
   int atomic_out;       // 1: red.add into D (split-K partial sums)
+  int hi_alt;           // 3xTF32: alternate the leading term between two accumulators
   int* error_flag;
 };
 
@@ -420,8 +422,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // and the leading term alternates between two accumulators to halve its chain length;
         // the epilogue adds the three in fp32 (round to nearest).
         const uint32_t acc_lo_first = (it > 0 || j > 0) ? 1u : 0u;
-        const uint32_t acc_hi_first = (it > 1 || j > 0) ? 1u : 0u;
-        const uint32_t acc_hi = tmem_acc + (uint32_t)((it & 1) * kBN);
+        const uint32_t acc_hi_first = (it > (p.hi_alt ? 1 : 0) || j > 0) ? 1u : 0u;
+        const uint32_t acc_hi = tmem_acc + (uint32_t)((p.hi_alt ? (it & 1) : 0) * kBN);
         const uint32_t acc_lo = tmem_acc + 2u * kBN;
         asm volatile(
             "{\n\t.reg .pred p, q, t;\n\t"
@@ -485,7 +487,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32);
         tmem_ld32(taddr, r);
         tmem_ld32(taddr + 2u * kBN, r2);
-        if (total_iters > 1) tmem_ld32(taddr + kBN, r1);
+        if (total_iters > 1 && p.hi_alt) tmem_ld32(taddr + kBN, r1);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (m < p.M) {
           const int nc = n0 + c * 32;
@@ -493,7 +495,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float acc = __uint_as_float(r[j]);
-            if (total_iters > 1) acc += __uint_as_float(r1[j]);
+            if (total_iters > 1 && p.hi_alt) acc += __uint_as_float(r1[j]);
             v[j] = (acc + __uint_as_float(r2[j])) + bias_m;
             if (p.bias_mode == 2 && nc + j < p.N) v[j] += p.bias[nc + j];
             if (p.relu) v[j] = fmaxf(v[j], 0.f);
@@ -523,11 +525,482 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
+// ---- persistent 3xTF32 GEMM for the short-K 1x1 convolutions ------------------------------
+// The expanding / reducing 1x1 convolutions of a bottleneck have K = C_in of 64 .. 512, i.e. 2 .. 16
+// K blocks per 128 x 128 output tile: a one-tile-per-CTA kernel spends its time in the prologue
+// (barrier init, TMEM allocation, first TMA round trip) and in the 64 KB epilogue. Here one CTA
+// per SM walks a static tile list; the TMA ring runs across tile boundaries, the accumulators are
+// double-buffered in TMEM (2 x {hi, lo} x 128 columns = all 512) and four dedicated warps drain
+// tile t while the MMA thread accumulates tile t + 1.
+// A = W (K-major, rows = output channels), B = X (MN-major, pixels contiguous), batch = image.
+// Leading term in ONE accumulator: the tensor core accumulates with truncation, which costs
+// ~3e-9 relative per K step (measured, tools/x3_accuracy.py) - below fp32 rounding for K <= 512.
+constexpr int kGemmPThreads = 384;
+
+__global__ void __launch_bounds__(kGemmPThreads, 1)
+gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                              const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full[kStages3], s_ready[kStages3], s_empty[kStages3], s_acc_full[2],
+      s_acc_empty[2];
+  __shared__ uint32_t s_tmem_base;
+  __shared__ int s_fail;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tiles = (smem_addr(smem_raw) + 1023u) & ~1023u;
+  uint8_t* tiles_ptr = smem_raw + (tiles - smem_addr(smem_raw));
+  const int num_kb = (p.K + kBK - 1) / kBK;
+  const int m_tiles = (p.M + kBM - 1) / kBM, n_tiles = (p.N + kBN - 1) / kBN;
+  const int total_tiles = m_tiles * n_tiles * p.batch;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages3; ++s) {
+      bar_init(smem_addr(&s_full[s]), 1);
+      bar_init(smem_addr(&s_ready[s]), 4);
+      bar_init(smem_addr(&s_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      bar_init(smem_addr(&s_acc_full[b]), 1);
+      bar_init(smem_addr(&s_acc_empty[b]), 4);   // one arrival per epilogue warp
+    }
+    s_fail = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_addr(&s_tmem_base)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_acc = s_tmem_base;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles && !s_fail; tile += gridDim.x) {
+      const int mt = tile % m_tiles, nt = (tile / m_tiles) % n_tiles, z = tile / (m_tiles * n_tiles);
+      const int m0 = mt * kBM, n0 = nt * kBN;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % kStages3;
+        const uint32_t ph = (it / kStages3) & 1;
+        if (!bar_wait(smem_addr(&s_empty[s]), ph ^ 1)) {
+          s_fail = 1;
+          break;
+        }
+        const uint32_t full = smem_addr(&s_full[s]);
+        bar_expect_tx(full, 3 * kTileBytes);
+        const int k0 = kb * kBK;
+        const uint32_t a_tile = tiles + s * kStageBytes3, alo_tile = a_tile + kTileBytes,
+                       b_tile = a_tile + 2 * kTileBytes;
+        tma_load_3d(a_tile, &tmA, k0, m0, 0, full);
+        tma_load_3d(alo_tile, &tmAlo, k0, m0, 0, full);
+#pragma unroll
+        for (int j = 0; j < kBN / 32; ++j) tma_load_3d(b_tile + j * (kBK * 128), &tmB, n0 + 32 * j, k0, z, full);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(kBN >> 3) << 17) |
+                           ((uint32_t)(kBM >> 4) << 24);      // A K-major, B MN-major
+    int it = 0, t = 0;
+    for (int tile = blockIdx.x; tile < total_tiles && !s_fail; tile += gridDim.x, ++t) {
+      const int buf = t & 1;
+      if (!bar_wait(smem_addr(&s_acc_empty[buf]), ((t >> 1) & 1) ^ 1)) {
+        s_fail = 1;
+        break;
+      }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc_hi = tmem_acc + (uint32_t)(buf * 2 * kBN), acc_lo = acc_hi + kBN;
+      bool failed = false;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % kStages3;
+        const uint32_t ph = (it / kStages3) & 1;
+        if (!bar_wait(smem_addr(&s_ready[s]), ph)) {
+          s_fail = 1;
+          failed = true;
+          break;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_tile = tiles + s * kStageBytes3, alo_tile = a_tile + kTileBytes,
+                       b_tile = a_tile + 2 * kTileBytes, blo_tile = a_tile + 3 * kTileBytes;
+#pragma unroll
+        for (int j = 0; j < kBK / kUmmaK; ++j) {
+          const uint64_t da = desc_k_major(a_tile, j), dal = desc_k_major(alo_tile, j);
+          const uint64_t db = desc_mn_major(b_tile, j), dbl = desc_mn_major(blo_tile, j);
+          const uint32_t accumulate = (kb > 0 || j > 0) ? 1u : 0u;
+          asm volatile(
+              "{\n\t.reg .pred p, t;\n\t"
+              "setp.ne.b32 p, %7, 0;\n\t"
+              "setp.eq.b32 t, %6, %6;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %4, %6, p;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%1], %2, %5, %6, t;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %4, %6, p;\n\t}"
+              ::"r"(acc_hi), "r"(acc_lo), "l"(da), "l"(dal), "l"(db), "l"(dbl), "r"(idesc), "r"(accumulate)
+              : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_addr(&s_empty[s]))
+                     : "memory");
+      }
+      if (failed) break;
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_addr(&s_acc_full[buf]))
+                   : "memory");
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===== transform warps: B_lo = B - trunc_tf32(B) =====
+    const int tt = threadIdx.x - 128;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles && !s_fail; tile += gridDim.x) {
+      bool failed = false;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % kStages3;
+        const uint32_t ph = (it / kStages3) & 1;
+        if (!bar_wait(smem_addr(&s_full[s]), ph)) {
+          s_fail = 1;
+          failed = true;
+          break;
+        }
+        const float4* src = reinterpret_cast<const float4*>(tiles_ptr + s * kStageBytes3 + 2 * kTileBytes);
+        float4* dst = reinterpret_cast<float4*>(tiles_ptr + s * kStageBytes3 + 3 * kTileBytes);
+#pragma unroll
+        for (int j = 0; j < kTileBytes / 16 / 128; ++j) {
+          const float4 v = src[tt + j * 128];
+          dst[tt + j * 128] = make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z),
+                                          tf32_residual(v.w));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&s_ready[s])) : "memory");
+      }
+      if (failed) break;
+    }
+  } else if (warp >= 8) {
+    // ===== epilogue warps (TMEM lane quarter = warp - 8) =====
+    const int wq = warp - 8;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      const int mt = tile % m_tiles, nt = (tile / m_tiles) % n_tiles, z = tile / (m_tiles * n_tiles);
+      const int m0 = mt * kBM, n0 = nt * kBN;
+      const int buf = t & 1;
+      bool ok = bar_wait(smem_addr(&s_acc_full[buf]), (t >> 1) & 1);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) {
+        s_fail = 1;
+        break;
+      }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = m0 + wq * 32 + lane;
+      float* drow = p.D + (long long)z * p.d_batch_stride + (long long)m * p.ldd;
+      const float bias_m = (p.bias_mode == 1 && m < p.M) ? p.bias[m] : 0.f;
+#pragma unroll 1
+      for (int c = 0; c < kBN / 32; ++c) {
+        uint32_t r[32], r2[32];
+        const uint32_t taddr = tmem_acc + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * 2 * kBN + c * 32);
+        tmem_ld32(taddr, r);
+        tmem_ld32(taddr + kBN, r2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c == kBN / 32 - 1) {
+          // all TMEM reads of this buffer are done: hand it back before the global stores
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&s_acc_empty[buf]))
+                         : "memory");
+        }
+        if (m < p.M) {
+          const int nc = n0 + c * 32;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = (__uint_as_float(r[j]) + __uint_as_float(r2[j])) + bias_m;
+            if (p.relu) v[j] = fmaxf(v[j], 0.f);
+          }
+          float* dst = drow + nc;
+          if (nc + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nc + j < p.N) dst[j] = v[j];
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (s_fail) {
+    if ((threadIdx.x & 31) == 0 && p.error_flag) atomicExch(p.error_flag, 1);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(512) : "memory");
+  }
+}
+
 __global__ void __launch_bounds__(256)
 tf32_residual_kernel(const float* __restrict__ x, float* __restrict__ lo, uint64_t n) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     lo[i] = tf32_residual(x[i]);
+}
+
+// ---- 3x3 convolution (stride 1, pad 1) as a shifted-window implicit GEMM, 3xTF32 ----------
+// The calibration forward's k x k convolutions (forward_net.py:200-216 run them through ORT).
+// The input is first copied into a zero-bordered, channel-last layout
+//     Xp[q][ci],   q = img * Pp + (h + 1)(W + 2) + (w + 1),   Pp = (H + 2)(W + 2)
+// in which tap (kh, kw) of the filter is the SAME matrix shifted by (kh - 1)(W + 2) + (kw - 1)
+// ROWS. So the convolution is 9 * C_in / 32 accumulating GEMM steps
+//     D[q][co] += Xp[q + shift(tap)][ci-block] (K-major A: one TMA box at a shifted row coordinate,
+//                 rows outside the tensor zero-filled)  x  Wt[tap][co][ci-block]^T (K-major B)
+// (channel-last because a swizzled TMA box may start at any row but only at 16-byte multiples
+// along the contiguous dimension — measured, tools/probe/tma_probe.cu — and the taps shift by
+// single pixels). Pixels sit on the TMEM lanes: the epilogue's lanes are consecutive pixels, so
+// every store of an output channel is a coalesced row segment of the unpadded NCHW output;
+// border positions of the padded plane are computed and dropped (7 % extra at 56 x 56).
+// fp32 accuracy as gemm_tf32x3_kernel: A_lo formed in shared memory, B_lo = host residual.
+// Generalised to a tap table so that the same kernel runs
+//   3x3 stride 2  : the input is split into its four (row, column) parity planes, each with a
+//                   one-pixel top/left zero border; tap (kh, kw) reads plane ((kh+1)&1, (kw+1)&1)
+//                   at a shift of {-1, 0} rows / columns — no wasted outputs;
+//   1x1 stride 2  : one tap, plane (0, 0) without border (the gather is the "padding" copy).
+struct ConvParams {
+  int n_img, c_in, c_out, H, W, Wp;   // H, W: OUTPUT size; Wp: padded plane width
+  int plane;            // Pp = Hp * Wp
+  int origin;           // 1: one-pixel top/left border in the padded plane, 0: none
+  int n_taps;
+  int tap_shift[9];     // row offset of every tap in Xp (plane base + window shift)
+  int bn;               // output channels per CTA (64 or 128)
+  int hi_alt;           // alternate the leading term between two accumulators
+  long long q_total;    // n_img * Pp
+  float* Y;             // [n_img][c_out][H][W]
+  const float* bias;    // per output channel or null
+  int relu;
+  int* error_flag;
+};
+
+__global__ void __launch_bounds__(kGemm3Threads, 1)
+conv_taps_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                      const __grid_constant__ CUtensorMap tmWlo, const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full[kStages3], s_ready[kStages3], s_empty[kStages3], s_tmem_full;
+  __shared__ uint32_t s_tmem_base;
+  __shared__ int s_fail;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tiles = (smem_addr(smem_raw) + 1023u) & ~1023u;
+  uint8_t* tiles_ptr = smem_raw + (tiles - smem_addr(smem_raw));
+  const long long q0 = (long long)blockIdx.x * kBM;
+  const int co0 = blockIdx.y * p.bn;
+  const int num_kb = (p.c_in + kBK - 1) / kBK;
+  const int total_iters = p.n_taps * num_kb;
+  const uint32_t w_tile_bytes = (uint32_t)p.bn * 128u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages3; ++s) {
+      bar_init(smem_addr(&s_full[s]), 1);
+      bar_init(smem_addr(&s_ready[s]), 4);
+      bar_init(smem_addr(&s_empty[s]), 1);
+    }
+    bar_init(smem_addr(&s_tmem_full), 1);
+    s_fail = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_addr(&s_tmem_base)),
+                 "r"(kTmemCols3)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_acc = s_tmem_base;
+
+  // stage layout: X tile | X_lo (computed) | W tile | W_lo tile
+  if (warp == 0 && lane == 0) {
+    for (int it = 0; it < total_iters; ++it) {
+      const int s = it % kStages3;
+      const uint32_t ph = (it / kStages3) & 1;
+      if (!bar_wait(smem_addr(&s_empty[s]), ph ^ 1)) {
+        s_fail = 1;
+        break;
+      }
+      const uint32_t full = smem_addr(&s_full[s]);
+      bar_expect_tx(full, kTileBytes + 2 * w_tile_bytes);
+      const int kb = it / p.n_taps, tap = it - kb * p.n_taps;
+      const int k0 = kb * kBK;
+      const int shift = p.tap_shift[tap];
+      const uint32_t x_tile = tiles + s * kStageBytes3, w_tile = x_tile + 2 * kTileBytes,
+                     wlo_tile = x_tile + 3 * kTileBytes;
+      tma_load_3d(x_tile, &tmX, k0, (int)q0 + shift, 0, full);
+      tma_load_3d(w_tile, &tmW, k0, co0, tap, full);
+      tma_load_3d(wlo_tile, &tmWlo, k0, co0, tap, full);
+    }
+  } else if (warp == 1 && lane == 0) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) |
+                           ((uint32_t)(kBM >> 4) << 24);      // A and B both K-major
+    bool failed = false;
+    for (int it = 0; it < total_iters; ++it) {
+      const int s = it % kStages3;
+      const uint32_t ph = (it / kStages3) & 1;
+      if (!bar_wait(smem_addr(&s_ready[s]), ph)) {
+        s_fail = 1;
+        failed = true;
+        break;
+      }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t x_tile = tiles + s * kStageBytes3, xlo_tile = x_tile + kTileBytes,
+                     w_tile = x_tile + 2 * kTileBytes, wlo_tile = x_tile + 3 * kTileBytes;
+#pragma unroll
+      for (int j = 0; j < kBK / kUmmaK; ++j) {
+        const uint64_t da = desc_k_major(x_tile, j), dal = desc_k_major(xlo_tile, j);
+        const uint64_t db = desc_k_major(w_tile, j), dbl = desc_k_major(wlo_tile, j);
+        const uint32_t acc_lo_first = (it > 0 || j > 0) ? 1u : 0u;
+        const uint32_t acc_hi_first = (it > (p.hi_alt ? 1 : 0) || j > 0) ? 1u : 0u;
+        const uint32_t acc_hi = tmem_acc + (uint32_t)((p.hi_alt ? (it & 1) : 0) * kBN);
+        const uint32_t acc_lo = tmem_acc + 2u * kBN;
+        asm volatile(
+            "{\n\t.reg .pred p, q, t;\n\t"
+            "setp.ne.b32 p, %7, 0;\n\t"
+            "setp.ne.b32 q, %8, 0;\n\t"
+            "setp.eq.b32 t, %6, %6;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %4, %6, p;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%1], %2, %5, %6, t;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %4, %6, q;\n\t}"
+            ::"r"(acc_hi), "r"(acc_lo), "l"(da), "l"(dal), "l"(db), "l"(dbl), "r"(idesc), "r"(acc_lo_first),
+              "r"(acc_hi_first)
+            : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_addr(&s_empty[s]))
+                   : "memory");
+    }
+    if (!failed)
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_addr(&s_tmem_full))
+                   : "memory");
+  } else if (warp >= 4) {
+    const int t = threadIdx.x - 128;
+    for (int it = 0; it < total_iters; ++it) {
+      const int s = it % kStages3;
+      const uint32_t ph = (it / kStages3) & 1;
+      if (!bar_wait(smem_addr(&s_full[s]), ph)) {
+        s_fail = 1;
+        break;
+      }
+      const float4* src = reinterpret_cast<const float4*>(tiles_ptr + s * kStageBytes3);
+      float4* dst = reinterpret_cast<float4*>(tiles_ptr + s * kStageBytes3 + kTileBytes);
+#pragma unroll
+      for (int j = 0; j < kTileBytes / 16 / 128; ++j) {
+        const float4 v = src[t + j * 128];
+        dst[t + j * 128] = make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z),
+                                       tf32_residual(v.w));
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&s_ready[s])) : "memory");
+    }
+  }
+  __syncwarp();
+
+  // ===== epilogue: TMEM lane = padded pixel q, columns = output channels =====
+  bool ok = true;
+  if (warp < 4) {
+    ok = bar_wait(smem_addr(&s_tmem_full), 0);
+    ok = __all_sync(0xffffffffu, ok);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (ok) {
+      const long long q = q0 + warp * 32 + lane;
+      bool valid = q < p.q_total;
+      long long out_base = 0;
+      if (valid) {
+        const int img = (int)(q / p.plane);
+        const int r = (int)(q - (long long)img * p.plane);
+        const int hp = r / p.Wp, wp = r - hp * p.Wp;
+        const int ho = hp - p.origin, wo = wp - p.origin;
+        valid = ho >= 0 && ho < p.H && wo >= 0 && wo < p.W;
+        out_base = (((long long)img * p.c_out) * p.H + ho) * p.W + wo;
+      }
+      const long long ch_stride = (long long)p.H * p.W;
+#pragma unroll 1
+      for (int c = 0; c < p.bn / 32; ++c) {
+        uint32_t r[32], r1[32], r2[32];
+        const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32);
+        tmem_ld32(taddr, r);
+        if (total_iters > 1 && p.hi_alt) tmem_ld32(taddr + kBN, r1);
+        tmem_ld32(taddr + 2u * kBN, r2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (valid) {
+          const int cb = co0 + c * 32;
+          float* dst = p.Y + out_base + (long long)cb * ch_stride;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (cb + j < p.c_out) {
+              float v = __uint_as_float(r[j]);
+              if (total_iters > 1 && p.hi_alt) v += __uint_as_float(r1[j]);
+              v += __uint_as_float(r2[j]);
+              if (p.bias) v += __ldg(p.bias + cb + j);
+              if (p.relu) v = fmaxf(v, 0.f);
+              dst[(long long)j * ch_stride] = v;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!ok || s_fail) {
+    if ((threadIdx.x & 31) == 0 && p.error_flag) atomicExch(p.error_flag, 1);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(kTmemCols3)
+                 : "memory");
+  }
+}
+
+// X[img][c][H][W] -> Xp[(plane * n_img + img) * Pp + r][c] (channel-last), 32 x 32 tile transpose.
+// Plane (a, b) of a stride-s split holds X(s (hp - origin) + a, s (wp - origin) + b), zero outside.
+__global__ void __launch_bounds__(256)
+pad_plane_kernel(const float* __restrict__ x, float* __restrict__ xp, int n_img, int C, int H, int W, int stride,
+                 int origin, int Hp, int Wp) {
+  __shared__ float tile[32][33];
+  const int plane = Hp * Wp;
+  const int img = blockIdx.z % n_img, ab = blockIdx.z / n_img;
+  const int a = ab / stride, b = ab - a * stride;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r = r0 + tx;
+  int off = -1;
+  if (r < plane) {
+    const int hp = r / Wp, wp = r - hp * Wp;
+    const int h = stride * (hp - origin) + a, w = stride * (wp - origin) + b;
+    if (hp >= origin && wp >= origin && h < H && w < W) off = h * W + w;
+  }
+  const float* src = x + (long long)img * C * H * W;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k;
+    tile[ty + 8 * k][tx] = (off >= 0 && c < C) ? src[(long long)c * H * W + off] : 0.f;
+  }
+  __syncthreads();
+  float* dst = xp + ((long long)blockIdx.z * plane + r0) * C + c0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int rr = ty + 8 * k;
+    if (r0 + rr < plane && c0 + tx < C) dst[(long long)rr * C + tx] = tile[tx][rr];
+  }
 }
 
 // ---- host: tensor maps ----------------------------------------------------------------
@@ -582,6 +1055,26 @@ int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer
 }  // namespace dpl
 
 using namespace dpl;
+
+// Experiment switch (DPL_X3_ALT=0: one accumulator for the leading 3xTF32 term).
+static int x3_hi_alt() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DPL_X3_ALT");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
+
+// K up to which the 1x1-convolution GEMM takes the persistent kernel (DPL_X3_PERSISTENT_MAX_K, 0 = never).
+static int x3_persistent_max_k() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DPL_X3_PERSISTENT_MAX_K");
+    v = e ? atoi(e) : 512;
+  }
+  return v;
+}
 
 // a_major / b_major: 0 = K-major (element (row, k) at row * ld + k), 1 = MN-major (at k * ld + row).
 extern "C" int dpl_gemm_tf32(const float* d_a, int a_major, long long lda, long long a_batch_stride,
@@ -712,10 +1205,27 @@ extern "C" int dpl_gemm_tf32x3(const float* d_a, const float* d_a_lo, int a_majo
   p.bias_mode = bias_mode;
   p.relu = relu;
   p.atomic_out = 0;
+  p.hi_alt = x3_hi_alt();
   p.error_flag = d_error_flag;
   dim3 grid((M + kBM - 1) / kBM, (N + kBN - 1) / kBN, (unsigned)batch);
   const size_t smem = (size_t)kStages3 * kStageBytes3 + 1024;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a_major == 0 && b_major == 1 && !p.a_batched && bias_mode != 2 && K <= x3_persistent_max_k()) {
+    // short-K 1x1 convolution: persistent kernel, one CTA per SM
+    static bool attr_done_p = false;
+    if (!attr_done_p) {
+      int e = cuda_status(cudaFuncSetAttribute(gemm_tf32x3_persistent_kernel,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                          "cudaFuncSetAttribute(gemm_tf32x3_persistent_kernel)");
+      if (e) return e;
+      attr_done_p = true;
+    }
+    const long long total = (long long)grid.x * grid.y * grid.z;
+    const unsigned ctas = (unsigned)(total < sm_count() ? total : sm_count());
+    gemm_tf32x3_persistent_kernel<<<ctas, kGemmPThreads, smem, s>>>(tmA, tmAlo, tmB, p);
+    DPL_LAUNCH_CHECK("gemm_tf32x3_persistent_kernel");
+    return 0;
+  }
 #define DPL_GEMM3_LAUNCH(AMN, BMN)                                                                     \
   do {                                                                                                 \
     static bool attr_done = false;                                                                     \
@@ -738,5 +1248,89 @@ extern "C" int dpl_gemm_tf32x3(const float* d_a, const float* d_a_lo, int a_majo
     DPL_GEMM3_LAUNCH(true, true);
 #undef DPL_GEMM3_LAUNCH
   DPL_LAUNCH_CHECK("gemm_tf32x3_kernel");
+  return 0;
+}
+
+// Channel-last staging copy for dpl_conv_taps_tf32x3:
+//   d_xp[(plane * n_img + img) * Hp * Wp + hp * Wp + wp][c] = X[img][c][stride (hp - origin) + a][stride (wp - origin) + b]
+// (zero where that is outside the image or hp / wp < origin), plane = a * stride + b < n_planes.
+extern "C" int dpl_pad_plane_f32(const float* d_x, float* d_xp, int n_img, int channels, int H, int W, int stride,
+                                 int origin, int Hp, int Wp, int n_planes, void* stream) {
+  DPL_REQUIRE(d_x && d_xp, "null pointer");
+  DPL_REQUIRE(n_img > 0 && channels > 0 && H > 0 && W > 0 && Hp > 0 && Wp > 0, "empty problem");
+  DPL_REQUIRE(stride >= 1 && stride <= 4 && n_planes >= 1 && n_planes <= stride * stride, "stride / n_planes");
+  DPL_REQUIRE(origin == 0 || origin == 1, "origin must be 0 or 1");
+  DPL_REQUIRE((long long)n_img * n_planes <= 65535 && (channels + 31) / 32 <= 65535, "grid limit");
+  const long long plane = (long long)Hp * Wp;
+  DPL_REQUIRE(plane < (1ll << 30), "plane too large");
+  dim3 grid((unsigned)((plane + 31) / 32), (unsigned)((channels + 31) / 32), (unsigned)(n_img * n_planes));
+  pad_plane_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_xp, n_img, channels, H, W, stride,
+                                                                        origin, Hp, Wp);
+  DPL_LAUNCH_CHECK("pad_plane_kernel");
+  return 0;
+}
+
+// Tap-table convolution, fp32-accurate (3xTF32) on the tensor cores:
+//   Y[img][co][ho][wo] = bias[co] + sum_tap sum_ci Wt[tap][co][ci] * Xp[q + tap_shift[tap]][ci],
+//   q = img * Hp * Wp + (ho + origin) * Wp + (wo + origin)
+//   d_xp        staging copy from dpl_pad_plane_f32, [total_rows][c_in]
+//   d_w_taps    weights tap-major [n_taps][c_out][c_in]; d_w_taps_lo their dpl_tf32_residual_f32
+//   tap_shift   host array of n_taps row offsets (1 <= n_taps <= 9)
+extern "C" int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, const float* d_w_taps,
+                                    const float* d_w_taps_lo, float* d_y, int n_img, int c_in, int c_out, int Ho,
+                                    int Wo, int Hp, int Wp, int origin, int n_taps, const int* tap_shift,
+                                    const float* d_bias, int relu, int* d_error_flag, void* stream) {
+  DPL_REQUIRE(d_xp && d_w_taps && d_w_taps_lo && d_y && tap_shift, "null pointer");
+  DPL_REQUIRE(n_img > 0 && c_in > 0 && c_out > 0 && Ho > 0 && Wo > 0, "empty problem");
+  DPL_REQUIRE(n_taps >= 1 && n_taps <= 9, "1 <= n_taps <= 9");
+  DPL_REQUIRE(origin == 0 || origin == 1, "origin must be 0 or 1");
+  DPL_REQUIRE(Hp >= Ho + origin && Wp >= Wo + origin, "padded plane smaller than the output");
+  const long long plane = (long long)Hp * Wp;
+  const long long q_total = (long long)n_img * plane;
+  DPL_REQUIRE(total_rows >= q_total && total_rows < (1ll << 31) - 4096, "total_rows out of range");
+  if (c_in & 3) {
+    set_error("dpl_conv_taps_tf32x3: c_in must be a multiple of 4 (TMA stride alignment)");
+    return DPL_E_UNSUPPORTED;
+  }
+  CUtensorMap tmX, tmW, tmWlo;
+  int st = make_map(&tmX, d_xp, (uint64_t)c_in, (uint64_t)total_rows, 1, (uint64_t)c_in, 0, kBM, false);
+  if (st) return st;
+  const int bn = c_out <= 64 ? 64 : 128;
+  st = make_map(&tmW, d_w_taps, (uint64_t)c_in, (uint64_t)c_out, (uint64_t)n_taps, (uint64_t)c_in,
+                (uint64_t)c_out * c_in, (uint32_t)bn, false);
+  if (!st)
+    st = make_map(&tmWlo, d_w_taps_lo, (uint64_t)c_in, (uint64_t)c_out, (uint64_t)n_taps, (uint64_t)c_in,
+                  (uint64_t)c_out * c_in, (uint32_t)bn, false);
+  if (st) return st;
+  ConvParams p;
+  p.n_img = n_img;
+  p.c_in = c_in;
+  p.c_out = c_out;
+  p.H = Ho;
+  p.W = Wo;
+  p.Wp = Wp;
+  p.plane = (int)plane;
+  p.origin = origin;
+  p.n_taps = n_taps;
+  for (int t = 0; t < 9; ++t) p.tap_shift[t] = t < n_taps ? tap_shift[t] : 0;
+  p.bn = bn;
+  p.hi_alt = x3_hi_alt();
+  p.q_total = q_total;
+  p.Y = d_y;
+  p.bias = d_bias;
+  p.relu = relu;
+  p.error_flag = d_error_flag;
+  dim3 grid((unsigned)((q_total + kBM - 1) / kBM), (unsigned)((c_out + bn - 1) / bn), 1);
+  const size_t smem = (size_t)kStages3 * kStageBytes3 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    int e = cuda_status(cudaFuncSetAttribute(conv_taps_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem),
+                        "cudaFuncSetAttribute(conv_taps_tf32x3_kernel)");
+    if (e) return e;
+    attr_done = true;
+  }
+  conv_taps_tf32x3_kernel<<<grid, kGemm3Threads, smem, static_cast<cudaStream_t>(stream)>>>(tmX, tmW, tmWlo, p);
+  DPL_LAUNCH_CHECK("conv_taps_tf32x3_kernel");
   return 0;
 }

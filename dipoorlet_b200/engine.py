@@ -44,6 +44,9 @@ class Engine:
         self.params = {}
         self.zero_points = {}
         self._w_lo = {}            # tf32 residuals of the 1x1 / Gemm weights (3xTF32 operand)
+        self._w_taps = {}          # tap-major 3x3 filters + residuals
+        self._pad_scratch = None   # zero-bordered input copy of the 3x3 convolution (grow-only)
+        self.tc_conv3x3 = os.environ.get("DPL_ENGINE_CONV3X3", "1") != "0"
         self._tc_off = set()       # nodes the tensor-core tile could not address
         self.tensor_cores = os.environ.get("DPL_ENGINE_TCGEN05", "1") != "0"
         self.refresh_initializers()
@@ -55,6 +58,7 @@ class Engine:
         inits = self.g.model.graph.initializers
         for name in (names if names is not None else inits):
             self._w_lo.pop(name, None)
+            self._w_taps.pop(name, None)
             arr = inits[name]
             if arr.dtype == np.float64:
                 arr = arr.astype(np.float32)
@@ -152,10 +156,40 @@ class Engine:
                 and x.is_contiguous() and x.shape[1] % 4 == 0 and (x.shape[2] * x.shape[3]) % 4 == 0)
 
     def _residual(self, name, w2):
+        """TF32 residual of a weight; cached for initializers only (a weight produced by a
+        Q/DQ pair inside the graph is recomputed: it changes whenever its source does)."""
+        if name not in self.params:
+            return K.tf32_residual(w2.contiguous())
         lo = self._w_lo.get(name)
         if lo is None or lo.shape != w2.shape:
             lo = self._w_lo[name] = K.tf32_residual(w2.contiguous())
         return lo
+
+    def _taps(self, name, w):
+        """Tap-major copy + residual of a filter for dpl_conv_taps_tf32x3 (same caching rule)."""
+        if name not in self.params:
+            return K.conv_taps_prepare(w)
+        t = self._w_taps.get(name)
+        if t is None:
+            t = self._w_taps[name] = K.conv_taps_prepare(w)
+        return t
+
+    def _tc_conv_taps(self, node, x, w, stride, dil, lo, hi):
+        """(kernel, stride) when the convolution runs on dpl_conv_taps_tf32x3 — 3x3 / pad 1 with
+        stride 1 or 2, or 1x1 / stride 2 / unpadded; ungrouped, C_in a multiple of 4 — else None."""
+        if not (self.tensor_cores and self.tc_conv3x3 and x.is_cuda and node.name not in self._tc_off
+                and w.dim() == 4 and list(dil) == [1, 1] and node.attrs.get("group", 1) == 1
+                and x.is_contiguous() and x.shape[1] % 4 == 0 and x.shape[1] >= 16
+                and stride[0] == stride[1] and w.shape[2] == w.shape[3]):
+            return None
+        k, st = int(w.shape[2]), int(stride[0])
+        if k == 3 and st in (1, 2) and list(lo) == [1, 1] and list(hi) == [1, 1]:
+            return k, st
+        if k == 1 and st == 2 and not any(lo) and not any(hi):
+            return k, st
+        if k == 1 and st == 1 and not any(lo) and not any(hi) and (x.shape[2] * x.shape[3]) % 4:
+            return k, st      # e.g. 7 x 7 maps: rows of 49 floats are not TMA-addressable per image
+        return None
 
     def _host(self, name, env):
         """Small constant operands (Clip bounds, Reshape targets) read on the host without
@@ -177,6 +211,17 @@ class Engine:
                 try:    # 1x1 convolution as a 3xTF32 GEMM on the tcgen05 tile (fp32-accurate)
                     w2 = w.view(w.shape[0], w.shape[1])
                     return [K.conv1x1_forward_x3(x, w2, self._residual(node.input[1], w2), b)]
+                except K.GemmUnsupported:
+                    self._tc_off.add(node.name)
+            taps_cfg = self._tc_conv_taps(node, x, w, stride, dil, lo, hi)
+            if taps_cfg is not None:
+                try:
+                    taps, taps_lo = self._taps(node.input[1], w)
+                    need = K.ConvPlan(x.shape[0], x.shape[2], x.shape[3], *taps_cfg).total_rows * x.shape[1]
+                    if self._pad_scratch is None or self._pad_scratch.numel() < need:
+                        self._pad_scratch = torch.empty(need, dtype=torch.float32, device=x.device)
+                    return [K.conv_taps_forward_x3(x, taps, taps_lo, taps_cfg[0], taps_cfg[1], b,
+                                                   scratch=self._pad_scratch)]
                 except K.GemmUnsupported:
                     self._tc_off.add(node.name)
             if not sym:

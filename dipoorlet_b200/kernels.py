@@ -4,6 +4,8 @@ every function enqueues on torch's current CUDA stream and returns without synci
 Nothing here computes: no torch math on the data path, no CPU fallback. A missing
 `libdpl_b200.so` raises from `_lib.lib()`.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -430,3 +432,74 @@ def linear_forward_x3(x, w, w_lo=None, bias=None):
     y = torch.empty((nrow, out_f), dtype=torch.float32, device=x.device)
     return gemm_tf32x3(x, tf32_residual(x), 0, k, 0, w, 0, k, 0, y, out_f, 0, nrow, out_f, k, batch=1,
                        bias=bias, bias_mode=2 if bias is not None else 0)
+
+
+def conv_taps_prepare(w):
+    """Tap-major copy [kh*kw][co][ci] of a [co][ci][kh][kw] filter and its TF32 residual (once
+    per weight)."""
+    co, ci = w.shape[0], w.shape[1]
+    taps = w.permute(2, 3, 0, 1).reshape(-1, co, ci).contiguous()
+    return taps, tf32_residual(taps)
+
+
+conv3x3_prepare = conv_taps_prepare
+
+
+class ConvPlan:
+    """Staging geometry of dpl_conv_taps_tf32x3 for one (kernel, stride, input size)."""
+
+    def __init__(self, n, h, w, ksize, stride):
+        self.n, self.h, self.w, self.stride = n, h, w, stride
+        if ksize == 3 and stride == 1:
+            self.ho, self.wo, self.hp, self.wp, self.origin, self.planes = h, w, h + 2, w + 2, 1, 1
+            self.shifts = [(kh - 1) * self.wp + (kw - 1) for kh in range(3) for kw in range(3)]
+        elif ksize == 3 and stride == 2:
+            self.ho, self.wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+            self.hp, self.wp, self.origin, self.planes = self.ho + 1, self.wo + 1, 1, 4
+            rows = n * self.hp * self.wp
+            self.shifts = [(((kh + 1) & 1) * 2 + ((kw + 1) & 1)) * rows - (kh == 0) * self.wp - (kw == 0)
+                           for kh in range(3) for kw in range(3)]
+        elif ksize == 1 and stride in (1, 2):
+            self.ho, self.wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+            self.hp, self.wp, self.origin, self.planes = self.ho, self.wo, 0, 1
+            self.shifts = [0]
+        else:
+            raise GemmUnsupported("conv plan: kernel %d stride %d" % (ksize, stride))
+        self.total_rows = self.planes * n * self.hp * self.wp
+        self.c_shifts = (ctypes.c_int * len(self.shifts))(*self.shifts)
+
+
+def conv3x3_plane_pitch(h, w):
+    return (h + 2) * (w + 2)
+
+
+def conv_taps_forward_x3(x, taps, taps_lo, ksize, stride, bias=None, relu=False, out=None, scratch=None):
+    """fp32-accurate 3x3 (stride 1 or 2, pad 1) or strided 1x1 convolution on the tensor cores:
+    channel-last staging copy of x (dpl_pad_plane_f32), then the shifted-window GEMM."""
+    n, ci, hh, ww = x.shape
+    co = taps.shape[1]
+    plan = ConvPlan(n, hh, ww, ksize, stride)
+    need = plan.total_rows * ci
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(need, dtype=torch.float32, device=x.device)
+    check(lib().dpl_pad_plane_f32(x.data_ptr(), scratch.data_ptr(), n, ci, hh, ww, stride, plan.origin, plan.hp,
+                                  plan.wp, plan.planes, _stream()), "dpl_pad_plane_f32")
+    _count()
+    y = torch.empty((n, co, plan.ho, plan.wo), dtype=torch.float32, device=x.device) if out is None else out
+    dev = x.device
+    flag = _gemm_err.get(dev)
+    if flag is None:
+        flag = _gemm_err[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = lib().dpl_conv_taps_tf32x3(scratch.data_ptr(), plan.total_rows, taps.data_ptr(), taps_lo.data_ptr(),
+                                    y.data_ptr(), n, ci, co, plan.ho, plan.wo, plan.hp, plan.wp, plan.origin,
+                                    len(plan.shifts), plan.c_shifts, _lib._ptr(bias), int(bool(relu)),
+                                    flag.data_ptr(), _stream())
+    if st == 10003:
+        raise GemmUnsupported(lib().dpl_last_error().decode("utf-8", "replace"))
+    check(st, "dpl_conv_taps_tf32x3")
+    _count()
+    return y
+
+
+def conv3x3_forward_x3(x, taps, taps_lo, bias=None, relu=False, out=None, scratch=None):
+    return conv_taps_forward_x3(x, taps, taps_lo, 3, 1, bias, relu, out, scratch)

@@ -224,6 +224,28 @@ int dpl_gemm_tf32x3(const float* d_a, const float* d_a_lo, int a_major, long lon
                     int M, int N, int K, int batch, const float* d_bias, int bias_mode, int relu,
                     int* d_error_flag, void* stream);
 
+/* k x k / strided convolutions of the calibration forward (the Conv nodes that ORT executes in
+ * dipoorlet/forward_net.py:200-216), fp32-accurate (3xTF32) on the tcgen05 tensor cores as a
+ * shifted-window implicit GEMM over a channel-last staging copy of the input:
+ *   dpl_pad_plane_f32     Xp[(plane * n_img + img) * Hp * Wp + hp * Wp + wp][c] =
+ *                           X[img][c][stride (hp - origin) + a][stride (wp - origin) + b]   (0 outside),
+ *                         plane = a * stride + b < n_planes  (stride 1: one bordered plane; stride 2:
+ *                         the four parity planes)
+ *   dpl_conv_taps_tf32x3  Y[img][co][ho][wo] = bias[co] + sum_tap sum_ci Wt[tap][co][ci] *
+ *                           Xp[q + tap_shift[tap]][ci],  q = img * Hp * Wp + (ho + origin) * Wp + (wo + origin);
+ *                         d_w_taps tap-major [n_taps][c_out][c_in], d_w_taps_lo = dpl_tf32_residual_f32
+ *                         of it; tap_shift: HOST array of n_taps (<= 9) row offsets; c_in multiple of 4.
+ * 3x3 stride 1 pad 1:  Hp = H + 2, Wp = W + 2, origin 1, shift = (kh - 1) Wp + (kw - 1).
+ * 3x3 stride 2 pad 1:  Hp = Ho + 1, Wp = Wo + 1, origin 1, tap (kh, kw) -> plane ((kh + 1) & 1, (kw + 1) & 1),
+ *                      shift = plane * n_img * Hp * Wp - (kh == 0) * Wp - (kw == 0).
+ * 1x1 stride 2:        Hp = Ho, Wp = Wo, origin 0, one plane, one tap, shift 0. */
+int dpl_pad_plane_f32(const float* d_x, float* d_xp, int n_img, int channels, int H, int W, int stride,
+                      int origin, int Hp, int Wp, int n_planes, void* stream);
+int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, const float* d_w_taps,
+                         const float* d_w_taps_lo, float* d_y, int n_img, int c_in, int c_out, int Ho,
+                         int Wo, int Hp, int Wp, int origin, int n_taps, const int* tap_shift,
+                         const float* d_bias, int relu, int* d_error_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

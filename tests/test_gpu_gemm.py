@@ -75,7 +75,8 @@ def test_unsupported_alignment_is_reported(dpl_built):
         K.conv1x1_forward(x, w)
 
 
-@pytest.mark.parametrize("dims", [(3, 64, 256, 56), (2, 96, 40, 28), (4, 1024, 256, 14), (1, 8, 136, 12)])
+@pytest.mark.parametrize("dims", [(3, 64, 256, 56), (2, 96, 40, 28), (4, 1024, 256, 14), (1, 8, 136, 12),
+                                  (64, 64, 256, 28), (40, 512, 128, 14), (7, 256, 520, 10), (300, 32, 24, 6)])
 def test_conv1x1_forward_3xtf32_is_fp32_accurate(dpl_built, dims):
     """3xTF32 must sit at fp32 accuracy (the calibration forward is compared at 1e-5):
     error vs float64 no worse than ~2x the error of a plain fp32 convolution."""
@@ -87,8 +88,11 @@ def test_conv1x1_forward_3xtf32_is_fp32_accurate(dpl_built, dims):
     x = torch.randn((n, ci, hw, hw), device="cuda", generator=g)
     w = torch.randn((co, ci), device="cuda", generator=g) * 0.1
     b = torch.randn(co, device="cuda", generator=g)
-    o = K.conv1x1_forward_x3(x, w, K.tf32_residual(w), b)
+    # K <= 512 runs the persistent kernel (several tiles per CTA above 148 tiles), else one tile per CTA
+    out = torch.full((n, co, hw, hw), float("nan"), device="cuda")
+    o = K.conv1x1_forward_x3(x, w, K.tf32_residual(w), b, out=out)
     K.gemm_check_errors()
+    assert not torch.isnan(o).any()
     want = torch.einsum("oc,nchw->nohw", w.double(), x.double()) + b.double().view(1, -1, 1, 1)
     torch.backends.cudnn.allow_tf32 = False
     ref32 = F.conv2d(x, w.view(co, ci, 1, 1), b)
@@ -111,3 +115,63 @@ def test_linear_forward_3xtf32(dpl_built):
     want = x.double() @ w.double().t() + b.double()
     err = (y.double() - want).abs().max().item()
     assert err <= 1e-5 * want.abs().max().item(), err
+
+
+@pytest.mark.parametrize("n,ci,co,h,w", [(3, 64, 64, 56, 56), (2, 128, 128, 28, 28), (5, 256, 256, 14, 14),
+                                         (4, 512, 512, 7, 7), (2, 48, 40, 9, 11), (1, 8, 200, 5, 3)])
+def test_conv3x3_forward_3xtf32(dpl_built, n, ci, co, h, w):
+    """Shifted-window 3x3 convolution on the tensor cores vs a float64 reference: within 3x the
+    error of torch's own fp32 (non-TF32) convolution, i.e. fp32-accurate; every output element
+    written (NaN pre-fill), borders exact (zero padding)."""
+    import torch
+    import torch.nn.functional as F
+    from dipoorlet_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(n * 1000 + ci)
+    x = torch.randn((n, ci, h, w), device="cuda", generator=g)
+    wt = torch.randn((co, ci, 3, 3), device="cuda", generator=g) * 0.05
+    b = torch.randn(co, device="cuda", generator=g)
+    taps, taps_lo = K.conv3x3_prepare(wt)
+    out = torch.full((n, co, h, w), float("nan"), device="cuda")
+    o = K.conv3x3_forward_x3(x, taps, taps_lo, b, relu=False, out=out)
+    K.gemm_check_errors()
+    assert not torch.isnan(o).any()
+    want = F.conv2d(x.double(), wt.double(), b.double(), padding=1)
+    torch.backends.cudnn.allow_tf32 = False
+    ref32 = F.conv2d(x, wt, b, padding=1)
+    err = (o.double() - want).abs().max().item()
+    err32 = (ref32.double() - want).abs().max().item()
+    scale = want.abs().max().item()
+    assert err <= max(3 * err32, 2e-6 * scale), (err, err32, scale)
+    o2 = K.conv3x3_forward_x3(x, taps, taps_lo, None, relu=True)
+    K.gemm_check_errors()
+    want2 = F.conv2d(x.double(), wt.double(), None, padding=1).clamp_min(0)
+    assert (o2.double() - want2).abs().max().item() <= max(3 * err32, 2e-6 * scale)
+
+
+@pytest.mark.parametrize("n,ci,co,h,w,k,stride", [(3, 128, 128, 56, 56, 3, 2), (4, 256, 256, 28, 28, 3, 2),
+                                                  (2, 32, 48, 7, 9, 3, 2), (2, 64, 96, 15, 14, 3, 2),
+                                                  (3, 256, 512, 56, 56, 1, 2), (5, 1024, 2048, 14, 14, 1, 2),
+                                                  (2, 24, 40, 7, 5, 1, 2)])
+def test_conv_strided_3xtf32(dpl_built, n, ci, co, h, w, k, stride):
+    """Stride-2 3x3 (parity-plane split) and stride-2 1x1 (gather) convolutions on the same
+    tap-table kernel, vs float64; odd sizes exercise the plane borders."""
+    import torch
+    import torch.nn.functional as F
+    from dipoorlet_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(n * 1000 + ci + k)
+    x = torch.randn((n, ci, h, w), device="cuda", generator=g)
+    wt = torch.randn((co, ci, k, k), device="cuda", generator=g) * 0.05
+    b = torch.randn(co, device="cuda", generator=g)
+    taps, taps_lo = K.conv_taps_prepare(wt)
+    pad = 1 if k == 3 else 0
+    want = F.conv2d(x.double(), wt.double(), b.double(), stride=stride, padding=pad)
+    out = torch.full(tuple(want.shape), float("nan"), device="cuda")
+    o = K.conv_taps_forward_x3(x, taps, taps_lo, k, stride, b, out=out)
+    K.gemm_check_errors()
+    assert not torch.isnan(o).any()
+    torch.backends.cudnn.allow_tf32 = False
+    ref32 = F.conv2d(x, wt, b, stride=stride, padding=pad)
+    err = (o.double() - want).abs().max().item()
+    err32 = (ref32.double() - want).abs().max().item()
+    scale = want.abs().max().item()
+    assert err <= max(3 * err32, 2e-6 * scale), (err, err32, scale)

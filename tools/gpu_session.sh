@@ -23,6 +23,10 @@ for s in $STEPS; do
     batch)   for b in ${BATCHES:-32 128}; do timeout 600 python bench.py --steps 2 --warmup 3 --batch $b --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('batch', d['config']['forward_batch'], 'value', round(d['value']), 'e2e', round(d['e2e']['value']), 'hist frac', round(d['roofline']['frac'],3))"; done ;;
     ncuhist) timeout 600 ncu --set full --clock-control none --import-source on -k regex:'hist_lc3|segstats_tiles' -c 2 -f -o gpurun_out/prof_hist_b32 \
                  python tools/kbench.py --batch 32 --quick > gpurun_out/ncu_hist_run.log 2>&1; tail -2 gpurun_out/ncu_hist_run.log ;;
+    convbench) timeout 300 python tools/conv_bench.py > gpurun_out/conv_bench.log 2>&1; tail -6 gpurun_out/conv_bench.log ;;
+    convtest) timeout 300 python -m pytest tests/test_gpu_gemm.py -q -k 'conv3x3 or conv_strided or 3xtf32' > gpurun_out/conv_test.log 2>&1; tail -15 gpurun_out/conv_test.log ;;
+    engprof) timeout 300 python tools/engine_profile.py 64 > gpurun_out/engine_profile.log 2>&1; tail -22 gpurun_out/engine_profile.log
+             DPL_ENGINE_CONV3X3=0 PROFILE_TAG=_cudnn3x3 timeout 300 python tools/engine_profile.py 64 > gpurun_out/engine_profile_cudnn3x3.log 2>&1; tail -22 gpurun_out/engine_profile_cudnn3x3.log ;;
     smoke)   timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3 ;;
   esac
 done
