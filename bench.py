@@ -122,15 +122,26 @@ def host_workers(cap=64):
     return max(1, min(n, cap))
 
 
+def _sized_sample(model, procs, target_s=15.0, cap_per_worker=64):
+    """Images for one timed CPU run: a 1-image-per-worker probe sets the rate, then the sample
+    is sized for about `target_s` seconds of wall time (a whole number of images per worker)."""
+    from dipoorlet_b200 import workloads as W
+    from oracle import pipeline as P
+    probe = W.synthetic_images(procs, seed=1)
+    secs, done = P.timed_parallel(model, probe, "hist", procs, BINS, THRESHOLD)
+    per_worker = int(max(2, min(cap_per_worker, round(target_s / max(secs, 1e-3)))))
+    return per_worker * procs
+
+
 def cpu_baseline(sample, procs=None):
     """Oracle ("port") timed on host cores. Returns dict for the JSON line."""
     from dipoorlet_b200 import workloads as W
     from oracle import pipeline as P
     procs = procs or host_workers()
-    if sample <= 0:
-        sample = 2 * procs   # two images per worker amortise the process start-up
-    sample = (sample // procs) * procs if sample >= procs else sample
     model = W.build_resnet50(seed=0)
+    if sample <= 0:
+        sample = _sized_sample(model, procs)
+    sample = (sample // procs) * procs if sample >= procs else sample
     images = W.synthetic_images(sample, seed=0)
     secs, done = P.timed_parallel(model, images, "hist", procs, BINS, THRESHOLD)
     return {"value": done / secs, "unit": "images/s", "cores": min(procs, sample), "kind": "port",
@@ -145,10 +156,11 @@ def run_reference(args):
     if rank != 0:
         return
     procs = host_workers()
-    sample = args.cpu_sample or 2 * procs
     from dipoorlet_b200 import workloads as W
     from oracle import pipeline as P
     model = W.build_resnet50(seed=0)
+    # each step = a bounded sample sized for ~15 s on this box's cores
+    sample = args.cpu_sample or _sized_sample(model, procs)
     images = W.synthetic_images(sample, seed=0)
     for _ in range(min(args.warmup, 1)):
         P.timed_parallel(model, images[:procs], "hist", procs, BINS, THRESHOLD)
@@ -291,8 +303,8 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "images_per_gpu": n_img, "forward_batch": args.batch,
                    "l2": "inputs larger than L2: every timed kernel streams a %.1f GB batch of blobs "
                          "(126 MB L2)" % (4 * elems_per_img * args.batch / 1e9),
-                   "forward": ("1x1 conv / Gemm: libdpl_b200 tcgen05 3xTF32 GEMM (fp32-accurate); k x k, strided convs and pooling: "
-                               "torch/cuDNN fp32 stand-in (TF32 off)") if os.environ.get("DPL_ENGINE_TCGEN05", "1") != "0"
+                   "forward": ("1x1 / 3x3 / strided conv + Gemm: libdpl_b200 tcgen05 3xTF32 tiles (fp32-accurate); 7x7 stem conv, "
+                               "pooling, Relu, Add: torch/cuDNN fp32 stand-in (TF32 off)") if os.environ.get("DPL_ENGINE_TCGEN05", "1") != "0"
                    else "torch/cuDNN fp32 (TF32 off) stand-in producer",
                    "statistics": "libdpl_b200.so (K1 segstats, K2 histogram variant 7, K3 percentile)",
                    "resident_blobs": bool(resident_used["v"])},
@@ -300,7 +312,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_per_step,
                 "d2h_bytes_per_step": d2h["n"], "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "K2 dpl_hist_abs_f32 variant %d" % args.hist_variant, "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "K2 dpl_hist_abs_f32 variant %d" % (args.hist_variant or 7), "achieved": achieved, "peak": peak,
                      "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured"
                      else "fallback 6.65 TB/s", "unit": "GB/s", "frac": achieved / peak if peak else None,
                      # dram__bytes_read + dram__bytes_write of this kernel from one `ncu --set full` capture
@@ -315,6 +327,11 @@ def run_ours(args):
                      "ms_per_launch_min": float(np.min(hist_ms)) if hist_ms else None,
                      "ms_per_launch_max": float(np.max(hist_ms)) if hist_ms else None},
     }
+    # north_star: the job rate as a fraction of the HBM-read roofline of its two statistics passes
+    # (2 x 4 B x elements per image at the measured peak); the forward that produces the blobs is extra
+    job_roof = peak * 1e9 / (2 * 4 * elems_per_img) * world
+    line["hbm_read_roofline"] = {"images_per_s": job_roof, "frac": value / job_roof,
+                                 "bytes_per_image": 2 * 4 * elems_per_img}
     if not args.no_cpu_baseline and world == 1:
         try:
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
