@@ -45,7 +45,7 @@ SIGNATURES = {
     "dpl_hist_abs_f32": (_c_int, [_c_vp, _c_int, _c_u64, _c_vp, _c_int, _c_vp, _c_int, _c_vp]),
     "dpl_hist_percentile": (_c_int, [_c_vp, _c_int, _c_int, _c_dbl, _c_vp, _c_vp, _c_vp, _c_vp,
                                      _c_vp, _c_vp]),
-    "dpl_octav_scratch_bytes": (_c_size, [_c_u64]),
+    "dpl_octav_scratch_bytes": (_c_size, [_c_u64, _c_u64]),
     "dpl_octav_f32": (_c_int, [_c_vp, _c_int, _c_u64, _c_u64, _c_vp, _c_vp, _c_dbl, _c_int, _c_vp,
                                _c_vp, _c_vp, _c_size, _c_vp]),
     "dpl_fakequant_f32": (_c_int, [_c_vp, _c_vp, _c_u64, _c_vp, _c_vp, _c_int, _c_u64, _c_int,

@@ -64,8 +64,43 @@ __device__ __forceinline__ void block_reduce(PassAcc& a, double* s_sum, unsigned
   __syncthreads();
 }
 
+// Work order: segments sorted by decreasing length (longest processing time first), taken from an
+// atomic counter by whichever CTA is free. Segment lengths span 1000 ... 802 816 elements
+// (ResNet-50), so a static round-robin leaves CTAs with up to twice the mean work; LPT + dynamic
+// claiming bounds the imbalance by the time of one SHORT segment. One thread per blob ranks its
+// blob (n_blobs^2 / 2 comparisons of a table that sits in L1) and writes its segments' slots.
+__global__ void octav_order_kernel(const dpl_blob* __restrict__ blobs, int n_blobs,
+                                   uint32_t* __restrict__ order, unsigned int* __restrict__ counter) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) *counter = 0u;
+  if (b >= n_blobs) return;
+  const uint64_t len = blobs[b].seg_len, nseg = blobs[b].n_seg;
+  uint64_t start = 0;
+  for (int o = 0; o < n_blobs; ++o) {
+    const uint64_t lo = blobs[o].seg_len;
+    if (lo > len || (lo == len && o < b)) start += blobs[o].n_seg;
+  }
+  for (uint64_t i = 0; i < nseg; ++i) order[start + i] = (uint32_t)(blobs[b].seg_out_base + i);
+}
+
+// One element of a compaction pass: the warp agrees on who survives (ballot), survivors are
+// written back-to-back in (row, component, lane) order. 32-bit indices throughout: a warp's
+// sub-range is at most seg_len / 16 elements.
+#define DPL_OCT_VISIT(a_, ok_)                                          \
+  do {                                                                  \
+    const float _a = (a_);                                              \
+    const bool _g = (ok_) && (_a > s);                                  \
+    const unsigned _m = __ballot_sync(0xffffffffu, _g);                 \
+    if (_g) {                                                           \
+      blk += _a;                                                        \
+      wout[wr + __popc(_m & lt_mask)] = _a;                             \
+    }                                                                   \
+    wr += __popc(_m);                                                   \
+  } while (0)
+
 __global__ void __launch_bounds__(kOctThreads, kOctCtasPerSm)
-octav_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_t n_segments,
+octav_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint32_t n_segments,
+             const uint32_t* __restrict__ order, unsigned int* __restrict__ counter,
              const double* __restrict__ abssum, const uint64_t* __restrict__ nnz, double k_const,
              int max_iter, float* __restrict__ scratch, uint64_t scratch_stride,
              float* __restrict__ out_s, int* __restrict__ out_iters) {
@@ -75,116 +110,105 @@ octav_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_t n_segment
   __shared__ uint32_t s_wcnt[kOctWarps];
   __shared__ float s_tail_s;
   __shared__ int s_tail_it, s_tail_fallback;
+  __shared__ uint32_t s_work;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
   float* my_scratch = scratch + (uint64_t)blockIdx.x * scratch_stride;
 
-  for (uint64_t sg = blockIdx.x; sg < n_segments; sg += gridDim.x) {
+  for (;;) {
+    if (threadIdx.x == 0) s_work = atomicAdd(counter, 1u);
+    __syncthreads();
+    const uint32_t work = s_work;
+    __syncthreads();
+    if (work >= n_segments) break;
+    const uint64_t sg = order[work];
     const int b = find_blob<3>(blobs, n_blobs, sg);
     const uint64_t seg = sg - blobs[b].seg_out_base;
-    const uint64_t n = blobs[b].seg_len;
-    const float* x = reinterpret_cast<const float*>(blobs[b].ptr) + seg * n;
+    const uint32_t n = (uint32_t)blobs[b].seg_len;
+    const float* x = reinterpret_cast<const float*>(blobs[b].ptr) + seg * (uint64_t)n;
     // per-warp sub-range, multiple of 128 elements so that rows stay 512-byte coalesced
-    const uint64_t sub = ((n + kOctWarps - 1) / kOctWarps + 127) / 128 * 128;
-    const uint64_t w0 = min(n, (uint64_t)warp * sub), w1 = min(n, (uint64_t)(warp + 1) * sub);
+    const uint32_t sub = ((n + kOctWarps - 1) / kOctWarps + 127) / 128 * 128;
+    const uint32_t w0 = min(n, (uint32_t)warp * sub), w1 = min(n, (uint32_t)(warp + 1) * sub);
+    const uint32_t wlen = w1 - w0;
+    const float* xw = x + w0;
     float* wout = my_scratch + w0;
 
     // s0 = abs_x.sum() / abs_x[abs_x > 0].size  (float32 / int -> float32)
     float s = __fdiv_rn((float)abssum[sg], (float)nnz[sg]);
-    uint64_t cnt = 0;      // survivors currently held in wout[0..cnt)
+    int it = 0;
+    if (!(s == s)) {
+      // NaN in the data, or an all-zero segment (0 / 0): every comparison of the reference's loop
+      // is false, num / den = 0 / 0 stays NaN and never converges (forward_net.py:325-330)
+      if (threadIdx.x == 0) {
+        out_s[sg] = s;
+        if (out_iters) out_iters[sg] = max_iter;
+      }
+      continue;
+    }
+    uint32_t cnt = 0;      // survivors currently held in wout[0..cnt)
     bool have = false;     // survivors valid for thresholds >= thr
     float thr = 0.f;
-    int it = 0;
     for (; it < max_iter; ++it) {
       PassAcc acc = {0.0, 0ull, 0ull};
-      const bool rescan = !have || !(s >= thr);
-      if (rescan) {
+      uint32_t wr = 0;
+      float blk = 0.f;  // float partial of one macro-step, folded into the double sum
+      if (!have || !(s >= thr)) {
         // stream the sub-range from the blob; keep |x| > s
-        uint64_t wr = 0;
-        float blk = 0.f;  // float partial of one macro-step, folded into the double sum
-        uint32_t le_cnt = 0;  // per-lane count(|x| <= s); explicit so that NaN behaves as in NumPy
-        const unsigned lt_mask = (1u << lane) - 1u;
-        auto visit = [&](float a, bool in) {
-          const bool g = in && (a > s);
-          const unsigned mg = __ballot_sync(0xffffffffu, g);
-          if (g) {
-            blk += a;
-            wout[wr + __popc(mg & lt_mask)] = a;
-          }
-          le_cnt += (in && (a <= s)) ? 1u : 0u;
-          wr += __popc(mg);
-        };
-        uint64_t i = w0;
-        if ((reinterpret_cast<uintptr_t>(x + w0) & 15u) == 0) {
-          for (; i + 512 <= w1; i += 512) {  // 4 rows of 32 float4 = 2 KB in flight per warp
+        uint32_t i = 0;
+        if ((reinterpret_cast<uintptr_t>(xw) & 15u) == 0) {
+          const float4* x4 = reinterpret_cast<const float4*>(xw) + lane;
+          for (; i + 512 <= wlen; i += 512) {  // 4 rows of 32 float4 = 2 KB in flight per warp
             float4 v[4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
-              v[r] = ldg_stream4(reinterpret_cast<const float4*>(x + i + r * 128) + lane);
+            for (int r = 0; r < 4; ++r) v[r] = ldg_stream4(x4 + (i >> 2) + r * 32);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-              visit(fabsf(v[r].x), true);
-              visit(fabsf(v[r].y), true);
-              visit(fabsf(v[r].z), true);
-              visit(fabsf(v[r].w), true);
+              DPL_OCT_VISIT(fabsf(v[r].x), true);
+              DPL_OCT_VISIT(fabsf(v[r].y), true);
+              DPL_OCT_VISIT(fabsf(v[r].z), true);
+              DPL_OCT_VISIT(fabsf(v[r].w), true);
             }
             acc.sum += (double)blk;
             blk = 0.f;
           }
         }
-        for (; i < w1; i += 128) {  // 4 rows of 32 scalars
+        for (; i < wlen; i += 128) {  // 4 rows of 32 scalars
           float a[4];
           bool in[4];
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
-            const uint64_t j = i + r * 32 + lane;
-            in[r] = j < w1;
-            a[r] = in[r] ? fabsf(ldg_stream1(x + j)) : 0.f;
+            const uint32_t j = i + r * 32 + lane;
+            in[r] = j < wlen;
+            a[r] = in[r] ? fabsf(ldg_stream1(xw + j)) : 0.f;
           }
 #pragma unroll
-          for (int r = 0; r < 4; ++r) visit(a[r], in[r]);
+          for (int r = 0; r < 4; ++r) DPL_OCT_VISIT(a[r], in[r]);
           acc.sum += (double)blk;
           blk = 0.f;
         }
-        cnt = wr;
-        thr = s;
         have = true;
-        if (lane == 0) acc.gt = wr;
-        acc.le = le_cnt;
       } else {
         // survivors only, compacted in place: a write never passes the rows already read
-        uint64_t wr = 0;
-        float blk = 0.f;
-        const unsigned lt_mask = (1u << lane) - 1u;
-        for (uint64_t i = 0; i < cnt; i += 256) {  // 8 rows of 32 in flight
+        for (uint32_t i = 0; i < cnt; i += 256) {  // 8 rows of 32 in flight
           float a[8];
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
-            const uint64_t j = i + r * 32 + lane;
+            const uint32_t j = i + r * 32 + lane;
             a[r] = (j < cnt) ? __ldcg(wout + j) : 0.f;   // 0 never survives (s > 0)
           }
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const bool g = a[r] > s;
-            const unsigned mg = __ballot_sync(0xffffffffu, g);
-            if (g) {
-              blk += a[r];
-              wout[wr + __popc(mg & lt_mask)] = a[r];
-            }
-            wr += __popc(mg);
-          }
+          for (int r = 0; r < 8; ++r) DPL_OCT_VISIT(a[r], true);
           acc.sum += (double)blk;
           blk = 0.f;
           __syncwarp();
         }
-        cnt = wr;
-        thr = s;
-        if (lane == 0) acc.gt = wr;
       }
-      const bool was_rescan = rescan;
+      cnt = wr;
+      thr = s;
+      if (lane == 0) acc.gt = wr;
       block_reduce(acc, s_sum, s_gt, s_le);
-      // count(|x| <= s): explicit on a rescan (NaN-faithful), n - count(>) otherwise
-      const double c_le = was_rescan ? (double)acc.le : (double)(n - acc.gt);
-      const double den = k_const * c_le + (double)acc.gt;  // Python float
+      // count(|x| <= s) = n - count(|x| > s): the segment holds no NaN (s0 would be NaN)
+      const double den = k_const * (double)(n - acc.gt) + (double)acc.gt;  // Python float
       const float s_next = __fdiv_rn((float)acc.sum, (float)den);
       if (fabsf(s_next - s) < 1e-6f) break;
       s = s_next;
@@ -193,25 +217,24 @@ octav_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_t n_segment
       // update) would dominate: gather them once and let warp 0 finish with shuffles only.
       if (acc.gt <= (unsigned long long)kTailCap && it + 1 < max_iter) {
         __syncwarp();
-        if (lane == 0) s_wcnt[warp] = (uint32_t)cnt;
+        if (lane == 0) s_wcnt[warp] = cnt;
         __syncthreads();
         uint32_t off = 0;
         for (int w = 0; w < warp; ++w) off += s_wcnt[w];
-        for (uint64_t i = lane; i < cnt; i += 32) s_tail[off + i] = __ldcg(wout + i);
+        for (uint32_t i = lane; i < cnt; i += 32) s_tail[off + i] = __ldcg(wout + i);
         __syncthreads();
         if (warp == 0) {
           uint32_t m = (uint32_t)acc.gt;
           float s2 = s, thr2 = thr;
           int it2 = it + 1;
           int fallback = 0;
-          const unsigned lt_mask = (1u << lane) - 1u;
           for (; it2 < max_iter; ++it2) {
             if (!(s2 >= thr2)) {   // would need elements dropped earlier: hand back to the block
               fallback = 1;
               break;
             }
-            uint32_t wr = 0;
-            float blk = 0.f;
+            uint32_t wr2 = 0;
+            float blk2 = 0.f;
             for (uint32_t i = 0; i < m; i += 32) {
               const uint32_t j = i + lane;
               const float a = (j < m) ? s_tail[j] : 0.f;
@@ -219,14 +242,14 @@ octav_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_t n_segment
               const unsigned mg = __ballot_sync(0xffffffffu, g);
               __syncwarp();
               if (g) {
-                blk += a;
-                s_tail[wr + __popc(mg & lt_mask)] = a;
+                blk2 += a;
+                s_tail[wr2 + __popc(mg & lt_mask)] = a;
               }
-              wr += __popc(mg);
+              wr2 += __popc(mg);
               __syncwarp();
             }
-            const double sum = warp_sum((double)blk);
-            m = wr;
+            const double sum = warp_sum((double)blk2);
+            m = wr2;
             thr2 = s2;
             const double den2 = k_const * (double)(n - m) + (double)m;
             const float sn = __fdiv_rn((float)sum, (float)den2);
@@ -254,19 +277,26 @@ octav_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint64_t n_segment
       out_s[sg] = s;
       if (out_iters) out_iters[sg] = it;
     }
-    __syncthreads();
   }
 }
+#undef DPL_OCT_VISIT
 
 }  // namespace
 }  // namespace dpl
 
 using namespace dpl;
 
-extern "C" size_t dpl_octav_scratch_bytes(uint64_t max_seg_len) {
+namespace {
+inline uint64_t oct_stride(uint64_t max_seg_len) {
   const uint64_t sub = ((max_seg_len + kOctWarps - 1) / kOctWarps + 127) / 128 * 128;
-  const uint64_t stride = sub * kOctWarps + 128;
-  return (size_t)stride * 4 * (size_t)sm_count() * kOctCtasPerSm + 256;
+  return sub * kOctWarps + 128;
+}
+}  // namespace
+
+extern "C" size_t dpl_octav_scratch_bytes(uint64_t max_seg_len, uint64_t n_segments) {
+  // per-CTA survivor slices + the work order (uint32 per segment) + the work counter
+  return (size_t)oct_stride(max_seg_len) * 4 * (size_t)sm_count() * kOctCtasPerSm + 256 +
+         (size_t)n_segments * 4 + 256;
 }
 
 extern "C" int dpl_octav_f32(const dpl_blob* d_blobs, int n_blobs, uint64_t n_segments,
@@ -276,21 +306,27 @@ extern "C" int dpl_octav_f32(const dpl_blob* d_blobs, int n_blobs, uint64_t n_se
   DPL_REQUIRE(d_blobs && n_blobs > 0, "empty blob table");
   DPL_REQUIRE(d_abssum && d_nnz && d_s, "null pointer");
   DPL_REQUIRE(max_iter >= 0, "negative max_iter");
+  DPL_REQUIRE(max_seg_len < (1ull << 31) && n_segments < (1ull << 32), "segment too long / too many");
   if (n_segments == 0) return 0;
-  if (!d_scratch || scratch_bytes < dpl_octav_scratch_bytes(max_seg_len)) {
+  if (!d_scratch || scratch_bytes < dpl_octav_scratch_bytes(max_seg_len, n_segments)) {
     set_error("dpl_octav_f32: scratch too small (%zu < %zu)", scratch_bytes,
-              dpl_octav_scratch_bytes(max_seg_len));
+              dpl_octav_scratch_bytes(max_seg_len, n_segments));
     return DPL_E_WORKSPACE;
   }
-  const uint64_t sub = ((max_seg_len + kOctWarps - 1) / kOctWarps + 127) / 128 * 128;
-  const uint64_t stride = sub * kOctWarps + 128;
-  float* scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(d_scratch) + 255) &
-                                            ~(uintptr_t)255);
+  const uint64_t stride = oct_stride(max_seg_len);
   uint64_t grid = (uint64_t)sm_count() * kOctCtasPerSm;
   if (grid > n_segments) grid = n_segments;
-  octav_kernel<<<(unsigned)grid, kOctThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_blobs, n_blobs, n_segments, d_abssum, d_nnz, k_const, max_iter, scratch, stride, d_s,
-      d_iters);
+  uintptr_t p = (reinterpret_cast<uintptr_t>(d_scratch) + 255) & ~(uintptr_t)255;
+  float* scratch = reinterpret_cast<float*>(p);
+  p += (uintptr_t)stride * 4 * (uintptr_t)sm_count() * kOctCtasPerSm;
+  uint32_t* order = reinterpret_cast<uint32_t*>(p);
+  unsigned int* counter = reinterpret_cast<unsigned int*>((p + n_segments * 4 + 127) & ~(uintptr_t)127);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  octav_order_kernel<<<(n_blobs + 127) / 128, 128, 0, st>>>(d_blobs, n_blobs, order, counter);
+  DPL_LAUNCH_CHECK("octav_order_kernel");
+  octav_kernel<<<(unsigned)grid, kOctThreads, 0, st>>>(d_blobs, n_blobs, (uint32_t)n_segments, order,
+                                                       counter, d_abssum, d_nnz, k_const, max_iter,
+                                                       scratch, stride, d_s, d_iters);
   DPL_LAUNCH_CHECK("octav_kernel");
   return 0;
 }

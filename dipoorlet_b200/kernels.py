@@ -143,7 +143,7 @@ def octav(batch, seg_abssum, seg_nnz, k_const, out_s, out_iters=None, max_iter=2
     _need(seg_nnz, torch.int64, "seg_nnz")
     _need(out_s, torch.float32, "out_s")
     _need(out_iters, torch.int32, "out_iters")
-    need = lib().dpl_octav_scratch_bytes(batch.max_seg_len)
+    need = lib().dpl_octav_scratch_bytes(batch.max_seg_len, batch.n_segments)
     ws = (workspace or Workspace(batch.device)).get(need)
     check(lib().dpl_octav_f32(batch.table.data_ptr(), batch.n_blobs, batch.n_segments,
                               batch.max_seg_len, seg_abssum.data_ptr(), seg_nnz.data_ptr(),

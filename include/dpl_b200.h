@@ -105,13 +105,15 @@ int dpl_hist_percentile(const unsigned long long* d_counts, int n_stats, int bin
                         double threshold, const float* d_data_max, const float* d_blob_min,
                         const float* d_blob_max, float* d_clip, int* d_bin, void* stream);
 
-/* K4 — OCTAV fixed point per segment (the 'mse' calibrator): one persistent CTA per
- * segment, HBM read once, survivors {|x| > s} compacted into an L2-resident scratch.
+/* K4 — OCTAV fixed point per segment (the 'mse' calibrator): persistent CTAs claim
+ * segments longest-first from a device work queue; each segment is read from HBM once,
+ * survivors {|x| > s} are compacted into an L2-resident scratch slice.
  * Replaces forward_net_octav's NumPy loop (dipoorlet/forward_net.py:316-330).
  *   k_const = 1 / 4**8 / 3 / unsigned; d_s: float32[n_segments]; d_iters (optional):
  *   int32[n_segments] updates taken; needs d_abssum / d_nnz from dpl_segstats_f32 for
- *   s0 and a scratch of dpl_octav_scratch_bytes(longest seg_len) bytes. */
-size_t dpl_octav_scratch_bytes(uint64_t max_seg_len);
+ *   s0 and a scratch of dpl_octav_scratch_bytes(longest seg_len, n_segments) bytes.
+ *   A segment with a NaN (or no non-zero element: 0 / 0) yields NaN, as the reference. */
+size_t dpl_octav_scratch_bytes(uint64_t max_seg_len, uint64_t n_segments);
 int dpl_octav_f32(const dpl_blob* d_blobs, int n_blobs, uint64_t n_segments,
                   uint64_t max_seg_len, const double* d_abssum, const uint64_t* d_nnz,
                   double k_const, int max_iter, float* d_s, int* d_iters, void* d_scratch,
