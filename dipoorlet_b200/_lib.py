@@ -74,13 +74,18 @@ SIGNATURES = {
     "dpl_gemm_tf32x3": (_c_int, [_c_vp, _c_vp, _c_int, ctypes.c_longlong, ctypes.c_longlong, _c_vp, _c_int,
                                  ctypes.c_longlong, ctypes.c_longlong, _c_vp, ctypes.c_longlong,
                                  ctypes.c_longlong, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_int,
-                                 _c_vp, _c_vp]),
+                                 _c_vp, _c_vp, _c_vp]),
     "dpl_pad_plane_f32": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                    _c_int, _c_vp]),
     "dpl_conv_taps_tf32x3": (_c_int, [_c_vp, ctypes.c_longlong, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int,
                                       _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_int,
-                                      _c_vp, _c_vp]),
+                                      _c_vp, _c_vp, _c_vp]),
     "dpl_mix_drop_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_u64, _c_flt, _c_u64, _c_vp]),
+    "dpl_clip_f32": (_c_int, [_c_vp, _c_vp, _c_u64, _c_flt, _c_flt, _c_vp]),
+    "dpl_add_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_u64, _c_vp]),
+    "dpl_maxpool2d_f32": (_c_int, [_c_vp, _c_vp, _c_u64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                   _c_int, _c_int, _c_int, _c_int, _c_vp]),
+    "dpl_global_avgpool_f32": (_c_int, [_c_vp, _c_vp, _c_u64, _c_u64, _c_vp]),
 }
 
 

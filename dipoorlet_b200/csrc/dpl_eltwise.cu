@@ -1,0 +1,217 @@
+// Non-GEMM operators of the calibration forward: Relu / Clip, Add (+ the Relu that follows it),
+// MaxPool, GlobalAveragePool — the nodes onnxruntime executes one image at a time in the reference
+// (dipoorlet/forward_net.py:200-216). Each is a single streaming pass over a whole batch of blobs,
+// HBM bound: 16-byte loads with several in flight per thread, grid = SMs x 8 CTAs.
+// Every node output is a calibration blob, so outputs are always materialised; the fused
+// Add + Relu kernel writes BOTH blobs from one read of its operands.
+
+#include <math.h>
+
+#include "dpl_common.cuh"
+
+namespace dpl {
+namespace {
+
+constexpr int kEltThreads = 256;
+constexpr int kEltCtasPerSm = 8;
+
+__device__ __forceinline__ float clip1(float x, float lo, float hi) {
+  // torch.clamp / ONNX Clip semantics incl. NaN propagation (a NaN fails both comparisons)
+  float v = x < lo ? lo : x;
+  return v > hi ? hi : v;
+}
+
+__device__ __forceinline__ void st_stream4(float4* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kEltThreads, kEltCtasPerSm)
+clip_kernel(const float* __restrict__ x, float* __restrict__ y, uint64_t n, float lo, float hi, int vec) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t done = 0;
+  if (vec) {
+    const uint64_t n4 = n >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    uint64_t i = tid;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+      float4 v[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) v[r] = ldg_stream4(x4 + i + r * stride);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        st_stream4(y4 + i + r * stride, make_float4(clip1(v[r].x, lo, hi), clip1(v[r].y, lo, hi),
+                                                    clip1(v[r].z, lo, hi), clip1(v[r].w, lo, hi)));
+    }
+    for (; i < n4; i += stride) {
+      const float4 v = ldg_stream4(x4 + i);
+      st_stream4(y4 + i, make_float4(clip1(v.x, lo, hi), clip1(v.y, lo, hi), clip1(v.z, lo, hi),
+                                     clip1(v.w, lo, hi)));
+    }
+    done = n4 << 2;
+  }
+  for (uint64_t i = done + tid; i < n; i += stride) y[i] = clip1(x[i], lo, hi);
+}
+
+template <bool RELU>
+__global__ void __launch_bounds__(kEltThreads, kEltCtasPerSm)
+add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
+           float* __restrict__ yr, uint64_t n, int vec) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t done = 0;
+  if (vec) {
+    const uint64_t n4 = n >> 2;
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    float4* r4 = reinterpret_cast<float4*>(yr);
+    uint64_t i = tid;
+    for (; i + stride < n4; i += 2 * stride) {
+      float4 u[2], w[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        u[r] = ldg_stream4(a4 + i + r * stride);
+        w[r] = ldg_stream4(b4 + i + r * stride);
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float4 s = make_float4(u[r].x + w[r].x, u[r].y + w[r].y, u[r].z + w[r].z, u[r].w + w[r].w);
+        st_stream4(y4 + i + r * stride, s);
+        if (RELU)
+          st_stream4(r4 + i + r * stride, make_float4(clip1(s.x, 0.f, INFINITY), clip1(s.y, 0.f, INFINITY),
+                                                      clip1(s.z, 0.f, INFINITY), clip1(s.w, 0.f, INFINITY)));
+      }
+    }
+    for (; i < n4; i += stride) {
+      const float4 u = ldg_stream4(a4 + i), w = ldg_stream4(b4 + i);
+      const float4 s = make_float4(u.x + w.x, u.y + w.y, u.z + w.z, u.w + w.w);
+      st_stream4(y4 + i, s);
+      if (RELU)
+        st_stream4(r4 + i, make_float4(clip1(s.x, 0.f, INFINITY), clip1(s.y, 0.f, INFINITY),
+                                       clip1(s.z, 0.f, INFINITY), clip1(s.w, 0.f, INFINITY)));
+    }
+    done = n4 << 2;
+  }
+  for (uint64_t i = done + tid; i < n; i += stride) {
+    const float s = a[i] + b[i];
+    y[i] = s;
+    if (RELU) yr[i] = clip1(s, 0.f, INFINITY);
+  }
+}
+
+// One thread per output element, consecutive threads along Wo (coalesced stores; the k x k window
+// reads overlap between neighbours and are served by L1). Padding never wins (-inf), as in ONNX.
+__global__ void __launch_bounds__(256)
+maxpool2d_kernel(const float* __restrict__ x, float* __restrict__ y, uint64_t planes, int H, int W,
+                 int kh, int kw, int sh, int sw, int pt, int pl, int Ho, int Wo) {
+  const uint64_t total = planes * (uint64_t)Ho * Wo;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int wo = (int)(i % Wo);
+    const int ho = (int)((i / Wo) % Ho);
+    const uint64_t pidx = i / ((uint64_t)Wo * Ho);
+    const float* xp = x + pidx * (uint64_t)H * W;
+    const int h0 = ho * sh - pt, w0 = wo * sw - pl;
+    float m = -INFINITY;
+    bool nan = false;
+    for (int a = 0; a < kh; ++a) {
+      const int h = h0 + a;
+      if (h < 0 || h >= H) continue;
+      for (int c = 0; c < kw; ++c) {
+        const int w = w0 + c;
+        if (w < 0 || w >= W) continue;
+        const float v = __ldg(xp + (uint64_t)h * W + w);
+        nan |= (v != v);
+        m = v > m ? v : m;
+      }
+    }
+    y[i] = nan ? NAN : m;
+  }
+}
+
+// One warp per (image, channel) plane: fp32 lane partials, shuffle tree, one division.
+__global__ void __launch_bounds__(256)
+global_avgpool_kernel(const float* __restrict__ x, float* __restrict__ y, uint64_t planes, uint64_t hw) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t p = warp; p < planes; p += nwarps) {
+    const float* xp = x + p * hw;
+    float acc = 0.f;
+    for (uint64_t i = lane; i < hw; i += 32) acc += __ldg(xp + i);
+    acc = warp_sum(acc);
+    if (lane == 0) y[p] = acc / (float)hw;
+  }
+}
+
+inline unsigned elt_grid(uint64_t work_items) {
+  const uint64_t cap = (uint64_t)sm_count() * kEltCtasPerSm;
+  uint64_t g = (work_items + kEltThreads - 1) / kEltThreads;
+  if (g < 1) g = 1;
+  return (unsigned)(g < cap ? g : cap);
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+}  // namespace dpl
+
+using namespace dpl;
+
+extern "C" int dpl_clip_f32(const float* d_x, float* d_y, uint64_t n, float lo, float hi, void* stream) {
+  DPL_REQUIRE(d_x && d_y, "null pointer");
+  if (n == 0) return 0;
+  const int vec = aligned16(d_x) && aligned16(d_y);
+  clip_kernel<<<elt_grid(vec ? (n + 3) / 4 : n), kEltThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_x, d_y, n, lo, hi, vec);
+  DPL_LAUNCH_CHECK("clip_kernel");
+  return 0;
+}
+
+extern "C" int dpl_add_f32(const float* d_a, const float* d_b, float* d_y, float* d_y_relu, uint64_t n,
+                           void* stream) {
+  DPL_REQUIRE(d_a && d_b && d_y, "null pointer");
+  if (n == 0) return 0;
+  const int vec = aligned16(d_a) && aligned16(d_b) && aligned16(d_y) && (!d_y_relu || aligned16(d_y_relu));
+  const unsigned grid = elt_grid(vec ? (n + 3) / 4 : n);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d_y_relu)
+    add_kernel<true><<<grid, kEltThreads, 0, st>>>(d_a, d_b, d_y, d_y_relu, n, vec);
+  else
+    add_kernel<false><<<grid, kEltThreads, 0, st>>>(d_a, d_b, d_y, nullptr, n, vec);
+  DPL_LAUNCH_CHECK("add_kernel");
+  return 0;
+}
+
+extern "C" int dpl_maxpool2d_f32(const float* d_x, float* d_y, uint64_t planes, int H, int W, int kh,
+                                 int kw, int sh, int sw, int pad_top, int pad_left, int Ho, int Wo,
+                                 void* stream) {
+  DPL_REQUIRE(d_x && d_y, "null pointer");
+  DPL_REQUIRE(H > 0 && W > 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && Ho > 0 && Wo > 0, "bad geometry");
+  if (planes == 0) return 0;
+  const uint64_t total = planes * (uint64_t)Ho * Wo;
+  uint64_t grid = (total + 255) / 256;
+  const uint64_t cap = (uint64_t)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  maxpool2d_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_x, d_y, planes, H, W, kh, kw, sh, sw, pad_top, pad_left, Ho, Wo);
+  DPL_LAUNCH_CHECK("maxpool2d_kernel");
+  return 0;
+}
+
+extern "C" int dpl_global_avgpool_f32(const float* d_x, float* d_y, uint64_t planes, uint64_t hw,
+                                      void* stream) {
+  DPL_REQUIRE(d_x && d_y, "null pointer");
+  DPL_REQUIRE(hw > 0, "empty plane");
+  if (planes == 0) return 0;
+  uint64_t grid = (planes * 32 + 255) / 256;
+  const uint64_t cap = (uint64_t)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  global_avgpool_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_y, planes, hw);
+  DPL_LAUNCH_CHECK("global_avgpool_kernel");
+  return 0;
+}

@@ -50,7 +50,10 @@ struct GemmParams {
   int atomic_out;       // 1: red.add into D (split-K partial sums)
   int hi_alt;           // 3xTF32: alternate the leading term between two accumulators
   int* error_flag;
+  float* D2;            // optional second output max(D, 0) with D's layout (the Relu blob behind a Conv)
 };
+
+__device__ __forceinline__ float relu_keep_nan(float v) { return v < 0.f ? 0.f : v; }
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -501,14 +504,25 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (p.relu) v[j] = fmaxf(v[j], 0.f);
           }
           float* dst = drow + nc;
-          if (nc + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+          float* dst2 = p.D2 ? p.D2 + (drow - p.D) + nc : nullptr;
+          if (nc + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) &&
+              ((reinterpret_cast<uintptr_t>(dst2) & 15u) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (dst2) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(dst2 + j) = make_float4(relu_keep_nan(v[j]), relu_keep_nan(v[j + 1]),
+                                                                   relu_keep_nan(v[j + 2]), relu_keep_nan(v[j + 3]));
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) dst[j] = v[j];
+              if (nc + j < p.N) {
+                dst[j] = v[j];
+                if (dst2) dst2[j] = relu_keep_nan(v[j]);
+              }
           }
         }
       }
@@ -722,14 +736,25 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
             if (p.relu) v[j] = fmaxf(v[j], 0.f);
           }
           float* dst = drow + nc;
-          if (nc + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+          float* dst2 = p.D2 ? p.D2 + (drow - p.D) + nc : nullptr;
+          if (nc + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) &&
+              ((reinterpret_cast<uintptr_t>(dst2) & 15u) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (dst2) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(dst2 + j) = make_float4(relu_keep_nan(v[j]), relu_keep_nan(v[j + 1]),
+                                                                   relu_keep_nan(v[j + 2]), relu_keep_nan(v[j + 3]));
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) dst[j] = v[j];
+              if (nc + j < p.N) {
+                dst[j] = v[j];
+                if (dst2) dst2[j] = relu_keep_nan(v[j]);
+              }
           }
         }
       }
@@ -785,6 +810,7 @@ struct ConvParams {
   const float* bias;    // per output channel or null
   int relu;
   int* error_flag;
+  float* Y2;            // optional second output max(Y, 0) (the Relu blob behind the Conv)
 };
 
 __global__ void __launch_bounds__(kGemm3Threads, 1)
@@ -953,6 +979,7 @@ conv_taps_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
               if (p.bias) v += __ldg(p.bias + cb + j);
               if (p.relu) v = fmaxf(v, 0.f);
               dst[(long long)j * ch_stride] = v;
+              if (p.Y2) p.Y2[(dst - p.Y) + (long long)j * ch_stride] = relu_keep_nan(v);
             }
           }
         }
@@ -1113,6 +1140,7 @@ extern "C" int dpl_gemm_tf32(const float* d_a, int a_major, long long lda, long 
   p.bias_mode = bias_mode;
   p.relu = relu;
   p.error_flag = d_error_flag;
+  p.D2 = nullptr;
   unsigned gz;
   if (fold_batch) {
     if (split_k < 1) split_k = 1;
@@ -1170,7 +1198,7 @@ extern "C" int dpl_gemm_tf32x3(const float* d_a, const float* d_a_lo, int a_majo
                                long long a_batch_stride, const float* d_b, int b_major, long long ldb,
                                long long b_batch_stride, float* d_d, long long ldd, long long d_batch_stride,
                                int M, int N, int K, int batch, const float* d_bias, int bias_mode, int relu,
-                               int* d_error_flag, void* stream) {
+                               float* d_d_relu, int* d_error_flag, void* stream) {
   DPL_REQUIRE(d_a && d_a_lo && d_b && d_d, "null pointer");
   DPL_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "empty problem");
   DPL_REQUIRE(bias_mode == 0 || d_bias, "bias_mode without bias");
@@ -1207,6 +1235,7 @@ extern "C" int dpl_gemm_tf32x3(const float* d_a, const float* d_a_lo, int a_majo
   p.atomic_out = 0;
   p.hi_alt = x3_hi_alt();
   p.error_flag = d_error_flag;
+  p.D2 = d_d_relu;
   dim3 grid((M + kBM - 1) / kBM, (N + kBN - 1) / kBN, (unsigned)batch);
   const size_t smem = (size_t)kStages3 * kStageBytes3 + 1024;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1279,7 +1308,8 @@ extern "C" int dpl_pad_plane_f32(const float* d_x, float* d_xp, int n_img, int c
 extern "C" int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, const float* d_w_taps,
                                     const float* d_w_taps_lo, float* d_y, int n_img, int c_in, int c_out, int Ho,
                                     int Wo, int Hp, int Wp, int origin, int n_taps, const int* tap_shift,
-                                    const float* d_bias, int relu, int* d_error_flag, void* stream) {
+                                    const float* d_bias, int relu, float* d_y_relu, int* d_error_flag,
+                                    void* stream) {
   DPL_REQUIRE(d_xp && d_w_taps && d_w_taps_lo && d_y && tap_shift, "null pointer");
   DPL_REQUIRE(n_img > 0 && c_in > 0 && c_out > 0 && Ho > 0 && Wo > 0, "empty problem");
   DPL_REQUIRE(n_taps >= 1 && n_taps <= 9, "1 <= n_taps <= 9");
@@ -1320,6 +1350,7 @@ extern "C" int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, con
   p.bias = d_bias;
   p.relu = relu;
   p.error_flag = d_error_flag;
+  p.Y2 = d_y_relu;
   dim3 grid((unsigned)((q_total + kBM - 1) / kBM), (unsigned)((c_out + bn - 1) / bn), 1);
   const size_t smem = (size_t)kStages3 * kStageBytes3 + 1024;
   static bool attr_done = false;

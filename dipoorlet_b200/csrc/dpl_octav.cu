@@ -14,6 +14,7 @@
 // re-streamed from the blob (never observed on real activations; kept for exactness).
 
 #include <math.h>
+#include <stdlib.h>
 
 #include "dpl_common.cuh"
 
@@ -84,20 +85,30 @@ __global__ void octav_order_kernel(const dpl_blob* __restrict__ blobs, int n_blo
 }
 
 // One element of a compaction pass: the warp agrees on who survives (ballot), survivors are
-// written back-to-back in (row, component, lane) order. 32-bit indices throughout: a warp's
-// sub-range is at most seg_len / 16 elements.
-#define DPL_OCT_VISIT(a_, ok_)                                          \
-  do {                                                                  \
-    const float _a = (a_);                                              \
-    const bool _g = (ok_) && (_a > s);                                  \
-    const unsigned _m = __ballot_sync(0xffffffffu, _g);                 \
-    if (_g) {                                                           \
-      blk += _a;                                                        \
-      wout[wr + __popc(_m & lt_mask)] = _a;                             \
-    }                                                                   \
-    wr += __popc(_m);                                                   \
-  } while (0)
+// written back-to-back in (row, component, lane) order through a warp-uniform running pointer.
+// Inline PTX keeps the visit at 9 branch-free instructions (compare, ballot, mask, popc,
+// address = pointer + 4 * rank, predicated store, predicated add, popc, pointer advance); the
+// C++ form compiled to ~20 with a divergent branch and 64-bit index arithmetic per element.
+// A lane without an element passes 0, which never survives (s >= 0).
+__device__ __forceinline__ void oct_visit(float a, float s, unsigned lt_mask, float*& wptr, float& blk) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b32 m, t, c;\n\t.reg .b64 q;\n\t"
+      "setp.gt.f32 p, %2, %3;\n\t"
+      "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+      "and.b32 t, m, %4;\n\t"
+      "popc.b32 t, t;\n\t"
+      "mad.wide.u32 q, t, 4, %0;\n\t"
+      "@p st.global.f32 [q], %2;\n\t"
+      "@p add.f32 %1, %1, %2;\n\t"
+      "popc.b32 c, m;\n\t"
+      "mad.wide.u32 %0, c, 4, %0;\n\t}"
+      : "+l"(wptr), "+f"(blk)
+      : "f"(a), "f"(s), "r"(lt_mask)
+      : "memory");
+}
+#define DPL_OCT_VISIT(a_, ok_) oct_visit((ok_) ? (a_) : 0.f, s, lt_mask, wptr, blk)
 
+template <int ROWS>   // float4 rows a warp keeps in flight while streaming a segment
 __global__ void __launch_bounds__(kOctThreads, kOctCtasPerSm)
 octav_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint32_t n_segments,
              const uint32_t* __restrict__ order, unsigned int* __restrict__ counter,
@@ -150,19 +161,19 @@ octav_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint32_t n_segment
     float thr = 0.f;
     for (; it < max_iter; ++it) {
       PassAcc acc = {0.0, 0ull, 0ull};
-      uint32_t wr = 0;
-      float blk = 0.f;  // float partial of one macro-step, folded into the double sum
+      float* wptr = wout;   // next free survivor slot of this warp (warp-uniform)
+      float blk = 0.f;      // float partial of one macro-step, folded into the double sum
       if (!have || !(s >= thr)) {
         // stream the sub-range from the blob; keep |x| > s
         uint32_t i = 0;
         if ((reinterpret_cast<uintptr_t>(xw) & 15u) == 0) {
           const float4* x4 = reinterpret_cast<const float4*>(xw) + lane;
-          for (; i + 512 <= wlen; i += 512) {  // 4 rows of 32 float4 = 2 KB in flight per warp
-            float4 v[4];
+          for (; i + 128 * ROWS <= wlen; i += 128 * ROWS) {  // ROWS rows of 32 float4 in flight per warp
+            float4 v[ROWS];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) v[r] = ldg_stream4(x4 + (i >> 2) + r * 32);
+            for (int r = 0; r < ROWS; ++r) v[r] = ldg_stream4(x4 + (i >> 2) + r * 32);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int r = 0; r < ROWS; ++r) {
               DPL_OCT_VISIT(fabsf(v[r].x), true);
               DPL_OCT_VISIT(fabsf(v[r].y), true);
               DPL_OCT_VISIT(fabsf(v[r].z), true);
@@ -203,9 +214,9 @@ octav_kernel(const dpl_blob* __restrict__ blobs, int n_blobs, uint32_t n_segment
           __syncwarp();
         }
       }
-      cnt = wr;
+      cnt = (uint32_t)(wptr - wout);
       thr = s;
-      if (lane == 0) acc.gt = wr;
+      if (lane == 0) acc.gt = cnt;
       block_reduce(acc, s_sum, s_gt, s_le);
       // count(|x| <= s) = n - count(|x| > s): the segment holds no NaN (s0 would be NaN)
       const double den = k_const * (double)(n - acc.gt) + (double)acc.gt;  // Python float
@@ -324,9 +335,14 @@ extern "C" int dpl_octav_f32(const dpl_blob* d_blobs, int n_blobs, uint64_t n_se
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   octav_order_kernel<<<(n_blobs + 127) / 128, 128, 0, st>>>(d_blobs, n_blobs, order, counter);
   DPL_LAUNCH_CHECK("octav_order_kernel");
-  octav_kernel<<<(unsigned)grid, kOctThreads, 0, st>>>(d_blobs, n_blobs, (uint32_t)n_segments, order,
-                                                       counter, d_abssum, d_nnz, k_const, max_iter,
-                                                       scratch, stride, d_s, d_iters);
+  static const int rows = [] {
+    const char* e = getenv("DPL_OCTAV_ROWS");
+    return e ? atoi(e) : 8;   // 8: 1.227 ms, 4: 1.258 ms, 2: 1.413 ms per 3.4 GB batch (B200)
+  }();
+  auto kern = rows == 8 ? octav_kernel<8> : (rows == 2 ? octav_kernel<2> : octav_kernel<4>);
+  kern<<<(unsigned)grid, kOctThreads, 0, st>>>(d_blobs, n_blobs, (uint32_t)n_segments, order, counter,
+                                               d_abssum, d_nnz, k_const, max_iter, scratch, stride, d_s,
+                                               d_iters);
   DPL_LAUNCH_CHECK("octav_kernel");
   return 0;
 }

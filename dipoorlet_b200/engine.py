@@ -6,13 +6,16 @@ Replaces the reference's per-sample `ort.InferenceSession.run` with every node o
 promoted to a graph output and copied back to the host (dipoorlet/forward_net.py:195-216)
 and the per-node sessions of ActivationCache.forward_subnet (forward_net.py:81-128).
 
-1x1 convolutions and Gemm layers run on libdpl_b200's tcgen05 GEMM in 3xTF32 mode (fp32-accurate
-products on the TF32 tensor cores, dpl_gemm_tf32x3). STAND-IN NOTICE (SURVEY.md §7 step 5,
-§8 f2): the remaining dense operators (k x k / strided / depthwise convolutions, pooling) are
-still issued through torch's CUDA ops (cuDNN, true fp32: TF32 disabled), i.e. a library call
-playing the role onnxruntime's CUDA EP plays in the reference. The statistics,
-fake-quant and rounding kernels — the hot path this repo is about — are libdpl_b200.so.
-QuantizeLinear + DequantizeLinear pairs are executed as ONE fused K5 launch.
+1x1 / 3x3 / strided convolutions and Gemm layers run on libdpl_b200's tcgen05 tiles in 3xTF32 mode
+(fp32-accurate products on the TF32 tensor cores); Relu / Clip / Add (+ the Relu behind it) /
+MaxPool / GlobalAveragePool are libdpl_b200 streaming kernels (dpl_eltwise.cu). STAND-IN NOTICE
+(SURVEY.md §7 step 5, §8 f2): what the tiles do not cover yet (the 7x7 stem convolution,
+depthwise / grouped convolutions, rarely used operators) is still issued through torch's CUDA
+ops (cuDNN, true fp32: TF32 disabled), i.e. a library call playing the role onnxruntime's CUDA
+EP plays in the reference. QuantizeLinear + DequantizeLinear pairs are ONE fused K5 launch.
+
+Blob memory: when `engine.arena` is set (forward_net.CalibrationSession does) every node output is
+bump-allocated from that one slab instead of torch's caching allocator.
 """
 import os
 from collections import OrderedDict
@@ -49,9 +52,68 @@ class Engine:
         self.tc_conv3x3 = os.environ.get("DPL_ENGINE_CONV3X3", "1") != "0"
         self._tc_off = set()       # nodes the tensor-core tile could not address
         self.tensor_cores = os.environ.get("DPL_ENGINE_TCGEN05", "1") != "0"
+        self.native_ops = os.environ.get("DPL_ENGINE_NATIVE_OPS", "1") != "0"
+        # Relu blob written by the Conv epilogue (second store stream). Measured on B200 at batch 64: the
+        # Relu pass disappears (0.46 -> 0.07 ms) but the non-overlapped epilogues grow by more
+        # (convolutions 6.07 -> 6.66 ms), so it stays off until the epilogue overlaps the main loop.
+        self.fuse_conv_relu = os.environ.get("DPL_ENGINE_FUSE_CONV_RELU", "0") == "1"
+        self.arena = None          # kernels.BlobArena: where node outputs are allocated
         self.refresh_initializers()
         self.nodes = list(onnx_graph.model.graph.nodes)
         self._fused_q = set()
+        self._relu_after = None    # Add node name -> the Relu node fused with it
+
+    # ------------------------------------------------------------------ blob memory
+    def _new(self, shape, like):
+        """Output buffer for a node: from the arena when one is attached."""
+        if self.arena is not None and like.is_cuda:
+            try:
+                return self.arena.alloc(shape)
+            except MemoryError:
+                pass
+        return torch.empty(tuple(int(d) for d in shape), dtype=torch.float32, device=like.device)
+
+    def _adopt(self, v):
+        """Move a tensor produced by a library op into the arena (one extra copy)."""
+        if (self.arena is None or not torch.is_tensor(v) or not v.is_cuda or v.dtype != torch.float32
+                or v.untyped_storage().data_ptr() == self.arena.buf.untyped_storage().data_ptr()):
+            return v
+        try:
+            o = self.arena.alloc(v.shape)
+        except MemoryError:
+            return v
+        o.copy_(v)
+        return o
+
+    def _relu_out(self, node, like, env):
+        """Buffer for the fused Relu blob behind `node`, or None when there is nothing to fuse."""
+        if not self.native_ops or not self.fuse_conv_relu:
+            return None
+        relu = self._fusable_relu(node)
+        if relu is None or relu.output[0] in env:
+            return None
+        return self._new(like.shape, like)
+
+    def _publish_relu(self, node, r, env):
+        if r is not None:
+            env[self._fusable_relu(node).output[0]] = r
+
+    def _native(self, x):
+        return self.native_ops and torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 \
+            and x.is_contiguous()
+
+    def _fusable_relu(self, node):
+        """The Relu that is the single consumer of this Conv's / Add's output: its blob is written
+        by the producer's epilogue instead of a pass of its own."""
+        if self._relu_after is None:
+            self._relu_after = {}
+            for n in self.nodes:
+                if n.op_type not in ("Add", "Conv"):
+                    continue
+                cons = self.g.input_map.get(n.output[0], [])
+                if len(cons) == 1 and cons[0].op_type == "Relu" and n.output[0] not in self.g.network_outputs:
+                    self._relu_after[n.name] = cons[0]
+        return self._relu_after.get(node.name)
 
     def refresh_initializers(self, names=None):
         """(Re)upload initializers — after bias correction / rounding rewrote weights."""
@@ -106,7 +168,7 @@ class Engine:
                 outs = self._exec(node, env)
                 for o, v in zip(node.output, outs):
                     if o:
-                        env[o] = v
+                        env[o] = self._adopt(v)
                 if not want_all:
                     for t in node.input:
                         if t in remaining:
@@ -210,18 +272,27 @@ class Engine:
             if self._tc_conv_ok(node, x, w, stride, dil, lo, hi):
                 try:    # 1x1 convolution as a 3xTF32 GEMM on the tcgen05 tile (fp32-accurate)
                     w2 = w.view(w.shape[0], w.shape[1])
-                    return [K.conv1x1_forward_x3(x, w2, self._residual(node.input[1], w2), b)]
+                    out = self._new((x.shape[0], w.shape[0], x.shape[2], x.shape[3]), x)
+                    r = self._relu_out(node, out, env)
+                    y = K.conv1x1_forward_x3(x, w2, self._residual(node.input[1], w2), b, out=out, out_relu=r)
+                    self._publish_relu(node, r, env)
+                    return [y]
                 except K.GemmUnsupported:
                     self._tc_off.add(node.name)
             taps_cfg = self._tc_conv_taps(node, x, w, stride, dil, lo, hi)
             if taps_cfg is not None:
                 try:
                     taps, taps_lo = self._taps(node.input[1], w)
-                    need = K.ConvPlan(x.shape[0], x.shape[2], x.shape[3], *taps_cfg).total_rows * x.shape[1]
+                    plan = K.ConvPlan(x.shape[0], x.shape[2], x.shape[3], *taps_cfg)
+                    need = plan.total_rows * x.shape[1]
                     if self._pad_scratch is None or self._pad_scratch.numel() < need:
                         self._pad_scratch = torch.empty(need, dtype=torch.float32, device=x.device)
-                    return [K.conv_taps_forward_x3(x, taps, taps_lo, taps_cfg[0], taps_cfg[1], b,
-                                                   scratch=self._pad_scratch)]
+                    out = self._new((x.shape[0], w.shape[0], plan.ho, plan.wo), x)
+                    r = self._relu_out(node, out, env)
+                    y = K.conv_taps_forward_x3(x, taps, taps_lo, taps_cfg[0], taps_cfg[1], b,
+                                               scratch=self._pad_scratch, out=out, out_relu=r)
+                    self._publish_relu(node, r, env)
+                    return [y]
                 except K.GemmUnsupported:
                     self._tc_off.add(node.name)
             if not sym:
@@ -238,6 +309,8 @@ class Engine:
                                        a.get("output_padding", [0] * nd), a.get("group", 1),
                                        a.get("dilations", [1] * nd))]
         if op == "Relu":
+            if self._native(x):
+                return [K.clip(x, 0.0, float("inf"), out=self._new(x.shape, x))]
             return [torch.relu(x)]
         if op == "Clip":
             lo = a.get("min")
@@ -246,6 +319,9 @@ class Engine:
                 lo = float(self._host(node.input[1], env).reshape(-1)[0])
             if len(node.input) > 2 and node.input[2]:
                 hi = float(self._host(node.input[2], env).reshape(-1)[0])
+            if self._native(x):
+                return [K.clip(x, float("-inf") if lo is None else lo, float("inf") if hi is None else hi,
+                               out=self._new(x.shape, x))]
             return [torch.clamp(x, lo, hi)]
         if op in ("MaxPool", "AveragePool"):
             nd = x.dim() - 2
@@ -253,6 +329,16 @@ class Engine:
             stride = a.get("strides", [1] * nd)
             sym, lo, hi = _sym_pads(a.get("pads", [0] * (2 * nd)), nd)
             ceil_mode = bool(a.get("ceil_mode", 0))
+            if op == "MaxPool" and nd == 2 and self._native(x) and list(a.get("dilations", [1, 1])) == [1, 1]:
+                def osz(n, k_, s_, p0, p1):
+                    v = n + p0 + p1 - k_
+                    o = (-(-v // s_) if ceil_mode else v // s_) + 1
+                    if ceil_mode and (o - 1) * s_ >= n + p0:   # the last window must start inside
+                        o -= 1
+                    return o
+                ho, wo = osz(x.shape[2], k[0], stride[0], lo[0], hi[0]), osz(x.shape[3], k[1], stride[1], lo[1], hi[1])
+                return [K.maxpool2d(x, k, stride, lo[0], lo[1], ho, wo,
+                                    out=self._new((x.shape[0], x.shape[1], ho, wo), x))]
             if op == "MaxPool":
                 if not sym:
                     x = F.pad(x, [p for i in reversed(range(nd)) for p in (lo[i], hi[i])],
@@ -263,9 +349,20 @@ class Engine:
                 raise NotImplementedError("AveragePool with asymmetric pads")
             return [F.avg_pool2d(x, k, stride, lo, ceil_mode, bool(a.get("count_include_pad", 0)))]
         if op == "GlobalAveragePool":
+            if self._native(x) and x.dim() >= 3:
+                return [K.global_avgpool(x, out=self._new(tuple(x.shape[:2]) + (1,) * (x.dim() - 2), x))]
             return [x.mean(dim=tuple(range(2, x.dim())), keepdim=True)]
         if op in ("Add", "Sub", "Mul", "Div"):
             y = self._val(node.input[1], env)
+            if op == "Add" and self._native(x) and self._native(y) and x.shape == y.shape:
+                relu = self._fusable_relu(node)
+                if relu is not None and relu.output[0] not in env:
+                    # the block's Add and the Relu behind it: both blobs from one read of the operands
+                    r = self._new(x.shape, x)
+                    out = K.add(x, y, out=self._new(x.shape, x), out_relu=r)
+                    env[relu.output[0]] = r
+                    return [out]
+                return [K.add(x, y, out=self._new(x.shape, x))]
             return [{"Add": torch.add, "Sub": torch.sub, "Mul": torch.mul, "Div": torch.div}[op](x, y)]
         if op == "Flatten":
             ax = a.get("axis", 1)
@@ -280,7 +377,7 @@ class Engine:
                 if (self.tensor_cores and x.is_cuda and node.name not in self._tc_off and x.dim() == 2
                         and x.shape[1] % 4 == 0 and x.is_contiguous()):
                     try:
-                        return [K.linear_forward_x3(x, w, None, c)]
+                        return [K.linear_forward_x3(x, w, None, c, out=self._new((x.shape[0], w.shape[0]), x))]
                     except K.GemmUnsupported:
                         self._tc_off.add(node.name)
                 return [F.linear(x, w, c)]

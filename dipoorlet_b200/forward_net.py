@@ -135,6 +135,7 @@ class CalibrationSession:
         self.in_shapes = {n: _per_image_shape(onnx_graph, n) for n in onnx_graph.network_inputs}
         self.h2d_bytes = 0
         self._copy_stream = None
+        self.arena = None
         f32 = dict(dtype=torch.float32, device=dev)
         self.blob_min = torch.full((self.n_stats,), float("inf"), **f32)
         self.blob_max = torch.full((self.n_stats,), float("-inf"), **f32)
@@ -160,6 +161,30 @@ class CalibrationSession:
     def _ranges(self):
         return [(b0, min(b0 + self.batch_size, self.ed)) for b0 in range(self.st, self.ed, self.batch_size)]
 
+    def _batch_bytes(self, b):
+        """Arena bytes of one forward batch of b images: every blob, 256-byte aligned."""
+        al = K.BlobArena.ALIGN
+        total = 0
+        for n in self.names:
+            if n in self.g.tensor_name_shape_map:
+                nb = 4 * b * int(np.prod(self.g.get_tensor_shape(n)[1:]))
+                total += (nb + al - 1) // al * al
+        return total + (total >> 6) + (8 << 20)   # slack for blobs whose shape the graph does not declare
+
+    def _attach_arena(self, ranges):
+        """One slab for the blobs of this pass: all batches when they stay resident for pass 2,
+        else one batch, recycled (stream order makes the reuse safe)."""
+        if self.device.type != "cuda":
+            return
+        if self.keep_resident:
+            need = sum(self._batch_bytes(b1 - b0) for b0, b1 in ranges)
+        else:
+            need = max(self._batch_bytes(b1 - b0) for b0, b1 in ranges)
+        if self.arena is None or self.arena.buf.numel() < need:
+            self.arena = None               # release before taking the larger slab
+            self.arena = K.BlobArena(need, self.device)
+        self.arena.reset()
+
     def _upload(self, b0, b1):
         feeds = {}
         for name, shape in self.in_shapes.items():
@@ -177,6 +202,7 @@ class CalibrationSession:
                 blobs = self.engine.run(self._upload(b0, b1), want="all")
                 yield b0 - self.st, b1 - self.st, K.BlobBatch([blobs[n] for n in self.names])
             return
+        self._attach_arena(ranges)
         main = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -206,11 +232,21 @@ class CalibrationSession:
         for i, (b0, b1) in enumerate(ranges):
             feeds, ev = nxt
             main.wait_event(ev)
-            if self.keep_resident:   # the input blob is kept for pass 2: detach it from the staging buffer
-                feeds = {k: v.clone() for k, v in feeds.items()}
+            if not self.keep_resident:
+                self.arena.reset()
+            else:   # the input blob is kept for pass 2: detach it from the staging buffer
+                kept = {}
+                for k, v in feeds.items():
+                    kept[k] = self.arena.alloc(v.shape)
+                    kept[k].copy_(v)
+                feeds = kept
             if i + 1 < len(ranges):
                 nxt = prefetch((i + 1) & 1, ranges[i + 1])
-            blobs = self.engine.run(feeds, want="all")
+            self.engine.arena = self.arena
+            try:
+                blobs = self.engine.run(feeds, want="all")
+            finally:
+                self.engine.arena = None
             yield b0 - self.st, b1 - self.st, K.BlobBatch([blobs[n] for n in self.names])
 
     # -- pass 1: min / max (+ moments for OCTAV) ------------------------------------
@@ -263,6 +299,8 @@ class CalibrationSession:
                 events.append((e0, e1, batch.elements * 4))
             del batch
         self.resident = None  # release the blobs
+        if self.keep_resident:
+            self.arena = None
         dist_helper.allreduce_sum(self.counts)
 
     def percentile_clip(self, bins, threshold):

@@ -284,6 +284,83 @@ def mix_drop(a, b, prob, seed, out=None):
     return y
 
 
+# ---- forward-engine operators (dpl_eltwise.cu) -------------------------------------------
+def clip(x, lo, hi, out=None):
+    """y = min(max(x, lo), hi); Relu is clip(x, 0, inf)."""
+    _need(x, torch.float32, "x")
+    y = torch.empty_like(x) if out is None else out
+    _need(y, torch.float32, "out")
+    check(lib().dpl_clip_f32(x.data_ptr(), y.data_ptr(), x.numel(), float(lo), float(hi), _stream()),
+          "dpl_clip_f32")
+    _count()
+    return y
+
+
+def add(a, b, out=None, out_relu=None):
+    """y = a + b (same shape); with `out_relu` also max(y, 0) from the same pass."""
+    _need(a, torch.float32, "a")
+    _need(b, torch.float32, "b")
+    assert a.shape == b.shape
+    y = torch.empty_like(a) if out is None else out
+    _need(y, torch.float32, "out")
+    _need(out_relu, torch.float32, "out_relu")
+    check(lib().dpl_add_f32(a.data_ptr(), b.data_ptr(), y.data_ptr(), _lib._ptr(out_relu), a.numel(),
+                            _stream()), "dpl_add_f32")
+    _count()
+    return y
+
+
+def maxpool2d(x, kernel, stride, pad_top, pad_left, ho, wo, out=None):
+    _need(x, torch.float32, "x")
+    n, c, h, w = x.shape
+    y = torch.empty((n, c, ho, wo), dtype=torch.float32, device=x.device) if out is None else out
+    _need(y, torch.float32, "out")
+    check(lib().dpl_maxpool2d_f32(x.data_ptr(), y.data_ptr(), n * c, h, w, int(kernel[0]), int(kernel[1]),
+                                  int(stride[0]), int(stride[1]), int(pad_top), int(pad_left), int(ho), int(wo),
+                                  _stream()), "dpl_maxpool2d_f32")
+    _count()
+    return y
+
+
+def global_avgpool(x, out=None):
+    _need(x, torch.float32, "x")
+    n, c = x.shape[0], x.shape[1]
+    hw = x.numel() // max(n * c, 1)
+    y = torch.empty((n, c) + (1,) * (x.dim() - 2), dtype=torch.float32, device=x.device) if out is None else out
+    _need(y, torch.float32, "out")
+    check(lib().dpl_global_avgpool_f32(x.data_ptr(), y.data_ptr(), n * c, hw, _stream()),
+          "dpl_global_avgpool_f32")
+    _count()
+    return y
+
+
+class BlobArena:
+    """One device slab, bump-allocated: every blob of a calibration forward lives in it.
+    A resident `hist` job holds ~110 GB of blobs; taking them from torch's caching allocator
+    costs one cudaMalloc per blob per batch on a cold process (measured: 21 s of a 22 s first
+    call), the slab costs one."""
+
+    ALIGN = 256
+
+    def __init__(self, nbytes, device):
+        self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        self.off = 0
+
+    def reset(self):
+        self.off = 0
+
+    def alloc(self, shape):
+        n = 4
+        for d in shape:
+            n *= int(d)
+        end = self.off + n
+        if end > self.buf.numel():
+            raise MemoryError("BlobArena exhausted (%d of %d bytes)" % (end, self.buf.numel()))
+        t = self.buf[self.off:end].view(torch.float32).view(tuple(int(d) for d in shape))
+        self.off = (end + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        return t
+
+
 class GemmUnsupported(RuntimeError):
     """The operands do not meet TMA's alignment rules; the caller keeps its other path."""
 
@@ -398,7 +475,7 @@ def tf32_residual(x):
 
 
 def gemm_tf32x3(a, a_lo, a_major, lda, a_batch_stride, b, b_major, ldb, b_batch_stride, d, ldd,
-                d_batch_stride, M, N, K, batch=1, bias=None, bias_mode=0, relu=False):
+                d_batch_stride, M, N, K, batch=1, bias=None, bias_mode=0, relu=False, d_relu=None):
     dev = d.device
     flag = _gemm_err.get(dev)
     if flag is None:
@@ -406,7 +483,8 @@ def gemm_tf32x3(a, a_lo, a_major, lda, a_batch_stride, b, b_major, ldb, b_batch_
     st = lib().dpl_gemm_tf32x3(a.data_ptr(), a_lo.data_ptr(), int(a_major), int(lda), int(a_batch_stride),
                                b.data_ptr(), int(b_major), int(ldb), int(b_batch_stride), d.data_ptr(),
                                int(ldd), int(d_batch_stride), int(M), int(N), int(K), int(batch),
-                               _lib._ptr(bias), int(bias_mode), int(bool(relu)), flag.data_ptr(), _stream())
+                               _lib._ptr(bias), int(bias_mode), int(bool(relu)), _lib._ptr(d_relu),
+                               flag.data_ptr(), _stream())
     if st == 10003:
         raise GemmUnsupported(lib().dpl_last_error().decode("utf-8", "replace"))
     check(st, "dpl_gemm_tf32x3")
@@ -414,22 +492,24 @@ def gemm_tf32x3(a, a_lo, a_major, lda, a_batch_stride, b, b_major, ldb, b_batch_
     return d
 
 
-def conv1x1_forward_x3(x, w, w_lo, bias=None, relu=False, out=None):
-    """fp32-accurate O[img][co][hw] = W[co][ci] x X[img][ci][hw] (+ bias[co]) on tensor cores."""
+def conv1x1_forward_x3(x, w, w_lo, bias=None, relu=False, out=None, out_relu=None):
+    """fp32-accurate O[img][co][hw] = W[co][ci] x X[img][ci][hw] (+ bias[co]) on tensor cores;
+    `out_relu` (same shape) also receives max(O, 0)."""
     n, ci, hh, ww = x.shape
     co = w.shape[0]
     hw = hh * ww
     o = torch.empty((n, co, hh, ww), dtype=torch.float32, device=x.device) if out is None else out
+    _need(out_relu, torch.float32, "out_relu")
     return gemm_tf32x3(w, w_lo, 0, ci, 0, x, 1, hw, ci * hw, o, hw, co * hw, co, hw, ci, batch=n,
-                       bias=bias, bias_mode=1 if bias is not None else 0, relu=relu)
+                       bias=bias, bias_mode=1 if bias is not None else 0, relu=relu, d_relu=out_relu)
 
 
-def linear_forward_x3(x, w, w_lo=None, bias=None):
+def linear_forward_x3(x, w, w_lo=None, bias=None, out=None):
     """fp32-accurate Y = X W^T (+ bias): A = X (its residual is computed here, X is small),
     B = W is split inside the kernel, so `w_lo` is not needed."""
     nrow, k = x.shape
     out_f = w.shape[0]
-    y = torch.empty((nrow, out_f), dtype=torch.float32, device=x.device)
+    y = torch.empty((nrow, out_f), dtype=torch.float32, device=x.device) if out is None else out
     return gemm_tf32x3(x, tf32_residual(x), 0, k, 0, w, 0, k, 0, y, out_f, 0, nrow, out_f, k, batch=1,
                        bias=bias, bias_mode=2 if bias is not None else 0)
 
@@ -473,7 +553,8 @@ def conv3x3_plane_pitch(h, w):
     return (h + 2) * (w + 2)
 
 
-def conv_taps_forward_x3(x, taps, taps_lo, ksize, stride, bias=None, relu=False, out=None, scratch=None):
+def conv_taps_forward_x3(x, taps, taps_lo, ksize, stride, bias=None, relu=False, out=None, scratch=None,
+                         out_relu=None):
     """fp32-accurate 3x3 (stride 1 or 2, pad 1) or strided 1x1 convolution on the tensor cores:
     channel-last staging copy of x (dpl_pad_plane_f32), then the shifted-window GEMM."""
     n, ci, hh, ww = x.shape
@@ -493,7 +574,7 @@ def conv_taps_forward_x3(x, taps, taps_lo, ksize, stride, bias=None, relu=False,
     st = lib().dpl_conv_taps_tf32x3(scratch.data_ptr(), plan.total_rows, taps.data_ptr(), taps_lo.data_ptr(),
                                     y.data_ptr(), n, ci, co, plan.ho, plan.wo, plan.hp, plan.wp, plan.origin,
                                     len(plan.shifts), plan.c_shifts, _lib._ptr(bias), int(bool(relu)),
-                                    flag.data_ptr(), _stream())
+                                    _lib._ptr(out_relu), flag.data_ptr(), _stream())
     if st == 10003:
         raise GemmUnsupported(lib().dpl_last_error().decode("utf-8", "replace"))
     check(st, "dpl_conv_taps_tf32x3")

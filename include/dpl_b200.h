@@ -218,13 +218,15 @@ int dpl_gemm_tf32(const float* d_a, int a_major, long long lda, long long a_batc
  *   a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo   (x_hi = top 19 bits, x_lo = x - x_hi),
  * for the calibration forward (activations must stay within fp32 rounding of the reference's
  * fp32 ORT path, dipoorlet/forward_net.py:200-216). d_a_lo = dpl_tf32_residual_f32(d_a) is
- * computed once per weight; the residual of B is formed in shared memory inside the kernel. */
+ * computed once per weight; the residual of B is formed in shared memory inside the kernel.
+ * d_d_relu (optional): a second output max(D, 0) with D's layout — the Relu node behind a Conv is
+ * a calibration blob of its own, so the epilogue writes both instead of a second pass. */
 int dpl_tf32_residual_f32(const float* d_x, float* d_lo, uint64_t n, void* stream);
 int dpl_gemm_tf32x3(const float* d_a, const float* d_a_lo, int a_major, long long lda,
                     long long a_batch_stride, const float* d_b, int b_major, long long ldb,
                     long long b_batch_stride, float* d_d, long long ldd, long long d_batch_stride,
                     int M, int N, int K, int batch, const float* d_bias, int bias_mode, int relu,
-                    int* d_error_flag, void* stream);
+                    float* d_d_relu, int* d_error_flag, void* stream);
 
 /* k x k / strided convolutions of the calibration forward (the Conv nodes that ORT executes in
  * dipoorlet/forward_net.py:200-216), fp32-accurate (3xTF32) on the tcgen05 tensor cores as a
@@ -246,7 +248,22 @@ int dpl_pad_plane_f32(const float* d_x, float* d_xp, int n_img, int channels, in
 int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, const float* d_w_taps,
                          const float* d_w_taps_lo, float* d_y, int n_img, int c_in, int c_out, int Ho,
                          int Wo, int Hp, int Wp, int origin, int n_taps, const int* tap_shift,
-                         const float* d_bias, int relu, int* d_error_flag, void* stream);
+                         const float* d_bias, int relu, float* d_y_relu, int* d_error_flag, void* stream);
+
+/* Non-GEMM operators of the calibration forward — the Relu / Clip / Add / MaxPool /
+ * GlobalAveragePool nodes onnxruntime executes per image in dipoorlet/forward_net.py:200-216 —
+ * each one streaming pass over a whole batch of blobs (HBM bound).
+ *   dpl_clip_f32            y = min(max(x, lo), hi), NaN propagates (Relu: lo = 0, hi = +inf)
+ *   dpl_add_f32             y = a + b; when d_y_relu is non-NULL also y_relu = max(y, 0): the
+ *                           residual Add and the Relu that follows it, both blobs from one read
+ *   dpl_maxpool2d_f32       planes = n_img * channels planes of H x W -> Ho x Wo, padding = -inf
+ *   dpl_global_avgpool_f32  y[plane] = mean of the plane's hw elements (fp32) */
+int dpl_clip_f32(const float* d_x, float* d_y, uint64_t n, float lo, float hi, void* stream);
+int dpl_add_f32(const float* d_a, const float* d_b, float* d_y, float* d_y_relu, uint64_t n,
+                void* stream);
+int dpl_maxpool2d_f32(const float* d_x, float* d_y, uint64_t planes, int H, int W, int kh, int kw,
+                      int sh, int sw, int pad_top, int pad_left, int Ho, int Wo, void* stream);
+int dpl_global_avgpool_f32(const float* d_x, float* d_y, uint64_t planes, uint64_t hw, void* stream);
 
 #ifdef __cplusplus
 }
