@@ -40,7 +40,7 @@ SIGNATURES = {
                                 ctypes.POINTER(_c_u64)]),
     "dpl_segstats_scratch_bytes": (_c_size, [_c_u64]),
     "dpl_segstats_f32": (_c_int, [_c_vp, _c_int, _c_u64, _c_u64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
-                                  _c_vp, _c_vp, _c_size, _c_vp]),
+                                  _c_vp, _c_vp, _c_size, _c_int, _c_vp]),
     "dpl_absmax_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_vp]),
     "dpl_hist_abs_f32": (_c_int, [_c_vp, _c_int, _c_u64, _c_vp, _c_int, _c_vp, _c_int, _c_vp]),
     "dpl_hist_percentile": (_c_int, [_c_vp, _c_int, _c_int, _c_dbl, _c_vp, _c_vp, _c_vp, _c_vp,
@@ -81,6 +81,10 @@ SIGNATURES = {
                                       _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_int,
                                       _c_vp, _c_vp, _c_vp]),
     "dpl_mix_drop_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_u64, _c_flt, _c_u64, _c_vp]),
+    "dpl_im2col_f32": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                _c_int, _c_int, _c_int, _c_vp]),
+    "dpl_conv1x1_px_tf32x3": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp,
+                                       _c_vp, _c_vp]),
     "dpl_clip_f32": (_c_int, [_c_vp, _c_vp, _c_u64, _c_flt, _c_flt, _c_vp]),
     "dpl_add_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_u64, _c_vp]),
     "dpl_maxpool2d_f32": (_c_int, [_c_vp, _c_vp, _c_u64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,

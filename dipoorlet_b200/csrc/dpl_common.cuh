@@ -79,6 +79,55 @@ __device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
     atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
+// Streaming 128-bit store: written once, read by a later kernel through L2.
+__device__ __forceinline__ void stg_stream4(float4* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// Counter-based uniform in [0, 1) keyed by (seed, element index): a 32-bit avalanche hash
+// (two multiply-xorshift rounds) of the index mixed with both halves of the seed. Not torch's
+// Philox stream - QDrop only needs an i.i.d. Bernoulli mask (brecq.py:169-170,
+// ada_quant_layer.py:28-36) that the backward pass can regenerate from the same (seed, index).
+// ~8 integer instructions per element (the 64-bit splitmix it replaces cost ~25).
+__device__ __forceinline__ float hash_u01(uint64_t seed, uint64_t i) {
+  uint32_t x = (uint32_t)i ^ (uint32_t)seed;
+  x += ((uint32_t)(i >> 32) ^ (uint32_t)(seed >> 32)) * 0x9E3779B9u;
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return (float)(x >> 8) * (1.0f / 16777216.0f);
+}
+
+// rint(x / s) with the IEEE-correct quotient, without paying for a full division per element.
+// r = RN(1 / s) (one __frcp_rn per tensor / channel row); q1 = x r refined by one FMA step is within
+// an ulp of x / s, so rint(q1) == rint(x / s) unless q1 sits within a few ulps of a rounding tie -
+// only then (about 1 element in 10^5) the exact __fdiv_rn is evaluated. Non-finite products keep
+// the plain quotient's behaviour (inf -> saturates in the caller's clamp, NaN propagates).
+__device__ __forceinline__ float rint_div(float x, float s, float r) {
+  const float q0 = __fmul_rn(x, r);
+  float q1 = __fmaf_rn(__fmaf_rn(-q0, s, x), r, q0);
+  if (!(fabsf(q0) < 3.0e38f)) q1 = q0;
+  float t = rintf(q1);
+  if (fabsf(fabsf(q1 - t) - 0.5f) <= fmaxf(fabsf(q1), 1.f) * 1e-6f) t = rintf(__fdiv_rn(x, s));
+  return t;
+}
+// True when rint_div may be used for this scale (normal, finite reciprocal); else use __fdiv_rn.
+__device__ __forceinline__ bool rint_div_ok(float s, float r) {
+  return fabsf(s) >= 1.17549435e-38f && fabsf(s) < 1.0e37f && fabsf(r) >= 1.17549435e-38f && fabsf(r) < 1.0e37f;
+}
+
+// Grid of the streaming elementwise kernels: 8 CTAs of 256 threads per SM, fewer for small inputs.
+inline unsigned stream_grid(uint64_t work_items) {
+  const uint64_t cap = (uint64_t)sm_count() * 8;
+  uint64_t g = (work_items + 255) / 256;
+  if (g < 1) g = 1;
+  return (unsigned)(g < cap ? g : cap);
+}
+
 // Last blob whose `begin` field (selected by FIELD: 4 = seg_tile_begin,
 // 5 = flat_tile_begin, as uint64 index into dpl_blob) is <= tile. Blobs with no
 // tiles share their begin with the next blob, so "last" skips them.

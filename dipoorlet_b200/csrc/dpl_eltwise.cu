@@ -57,7 +57,7 @@ clip_kernel(const float* __restrict__ x, float* __restrict__ y, uint64_t n, floa
 }
 
 template <bool RELU>
-__global__ void __launch_bounds__(kEltThreads, kEltCtasPerSm)
+__global__ void __launch_bounds__(kEltThreads, 4)   // 64 registers: four vectors in flight, no spills
 add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
            float* __restrict__ yr, uint64_t n, int vec) {
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -104,33 +104,33 @@ add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __re
 }
 
 // One thread per output element, consecutive threads along Wo (coalesced stores; the k x k window
-// reads overlap between neighbours and are served by L1). Padding never wins (-inf), as in ONNX.
+// reads overlap between neighbours and are served by L1). A CTA works inside one plane, so the index
+// arithmetic is two 32-bit divisions per output. Padding never wins (-inf), as in ONNX.
 __global__ void __launch_bounds__(256)
-maxpool2d_kernel(const float* __restrict__ x, float* __restrict__ y, uint64_t planes, int H, int W,
+maxpool2d_kernel(const float* __restrict__ x, float* __restrict__ y, uint32_t tiles_per_plane, int H, int W,
                  int kh, int kw, int sh, int sw, int pt, int pl, int Ho, int Wo) {
-  const uint64_t total = planes * (uint64_t)Ho * Wo;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int wo = (int)(i % Wo);
-    const int ho = (int)((i / Wo) % Ho);
-    const uint64_t pidx = i / ((uint64_t)Wo * Ho);
-    const float* xp = x + pidx * (uint64_t)H * W;
-    const int h0 = ho * sh - pt, w0 = wo * sw - pl;
-    float m = -INFINITY;
-    bool nan = false;
-    for (int a = 0; a < kh; ++a) {
-      const int h = h0 + a;
-      if (h < 0 || h >= H) continue;
-      for (int c = 0; c < kw; ++c) {
-        const int w = w0 + c;
-        if (w < 0 || w >= W) continue;
-        const float v = __ldg(xp + (uint64_t)h * W + w);
-        nan |= (v != v);
-        m = v > m ? v : m;
-      }
+  const uint32_t plane = blockIdx.x / tiles_per_plane;
+  const uint32_t tile = blockIdx.x - plane * tiles_per_plane;
+  const uint32_t idx = tile * 256u + threadIdx.x;
+  if (idx >= (uint32_t)(Ho * Wo)) return;
+  const int ho = (int)(idx / (uint32_t)Wo), wo = (int)(idx - (uint32_t)ho * (uint32_t)Wo);
+  const float* xp = x + (uint64_t)plane * (uint32_t)(H * W);
+  const int h0 = ho * sh - pt, w0 = wo * sw - pl;
+  float m = -INFINITY;
+  bool nan = false;
+  for (int a = 0; a < kh; ++a) {
+    const int h = h0 + a;
+    if (h < 0 || h >= H) continue;
+    const float* row = xp + h * W;
+    for (int c = 0; c < kw; ++c) {
+      const int w = w0 + c;
+      if (w < 0 || w >= W) continue;
+      const float v = __ldg(row + w);
+      nan |= (v != v);
+      m = v > m ? v : m;
     }
-    y[i] = nan ? NAN : m;
   }
+  y[(uint64_t)plane * (uint32_t)(Ho * Wo) + idx] = nan ? NAN : m;
 }
 
 // One warp per (image, channel) plane: fp32 lane partials, shuffle tree, one division.
@@ -193,12 +193,11 @@ extern "C" int dpl_maxpool2d_f32(const float* d_x, float* d_y, uint64_t planes, 
   DPL_REQUIRE(d_x && d_y, "null pointer");
   DPL_REQUIRE(H > 0 && W > 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && Ho > 0 && Wo > 0, "bad geometry");
   if (planes == 0) return 0;
-  const uint64_t total = planes * (uint64_t)Ho * Wo;
-  uint64_t grid = (total + 255) / 256;
-  const uint64_t cap = (uint64_t)sm_count() * 16;
-  if (grid > cap) grid = cap;
-  maxpool2d_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_x, d_y, planes, H, W, kh, kw, sh, sw, pad_top, pad_left, Ho, Wo);
+  DPL_REQUIRE((long long)H * W < (1ll << 31) && (long long)Ho * Wo < (1ll << 31), "plane too large");
+  const uint64_t tiles_per_plane = ((uint64_t)Ho * Wo + 255) / 256;
+  DPL_REQUIRE(planes * tiles_per_plane < (1ull << 31), "too many tiles");
+  maxpool2d_kernel<<<(unsigned)(planes * tiles_per_plane), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_x, d_y, (uint32_t)tiles_per_plane, H, W, kh, kw, sh, sw, pad_top, pad_left, Ho, Wo);
   DPL_LAUNCH_CHECK("maxpool2d_kernel");
   return 0;
 }

@@ -1030,6 +1030,286 @@ pad_plane_kernel(const float* __restrict__ x, float* __restrict__ xp, int n_img,
   }
 }
 
+
+// ---- pixel-major 1x1 convolution, 3xTF32, activations through TMEM ------------------------
+// Y[img][co][px] = bias[co] + sum_ci W[co][ci] * X[img][ci][px], straight from / to NCHW.
+// Orientation: the PIXELS sit on the M side (TMEM lanes), the output channels on N:
+//     D[px][co] += A[px][ci] * B[co][ci]^T
+//  * A = activations is the TMEM operand of tcgen05.mma ("TS" form): four transform warps read the
+//    landed X tile [32 ci][128 px] from shared memory (thread <-> pixel, consecutive lanes read
+//    consecutive words: conflict free, no swizzle needed because the tensor core never reads this
+//    tile), split it into the TF32 pattern and its residual in registers and tcgen05.st both
+//    into TMEM. Against the shared-memory form this removes the X_lo write, the three re-reads of
+//    the X tiles by the MMAs and the generic->async proxy fence: shared-memory traffic per K block
+//    drops from 176 KB to 72 KB (the 128 x 128 x 8 TF32 instruction with both operands in shared
+//    memory saturates the 128 B/clk port on its own).
+//  * B = weights, K-major, 128-byte swizzle, by TMA together with their host-side residual.
+//  * Epilogue lanes are consecutive pixels: every store of an output channel is one coalesced
+//    128-byte row segment of the NCHW output (the co-on-lanes orientation wrote 16 bytes to each
+//    of 32 rows per instruction).
+//  * 128 px x 64 co tiles, 256 TMEM columns (2 x {A_hi, A_lo} x 32 + {acc_hi, acc_lo} x 64) and
+//    97 KB of shared memory per CTA: two CTAs per SM, so one tile's epilogue overlaps the other's
+//    main loop without a persistent scheduler.
+constexpr int kPxBN = 64;
+constexpr int kPxStages = 3;
+constexpr int kPxXBytes = kBK * kBM * 4;                  // 16 KB, [32 ci][128 px], unswizzled
+constexpr int kPxWBytes = kPxBN * kBK * 4;                // 8 KB, [64 co][32 ci], SW128
+constexpr int kPxStageBytes = kPxXBytes + 2 * kPxWBytes;  // 32 KB
+constexpr int kPxThreads = 256;
+constexpr int kPxTmemCols = 256;
+
+struct PxParams {
+  int n_img, c_in, c_out, hw;
+  float* Y;
+  float* Y2;            // optional max(Y, 0)
+  const float* bias;
+  int* error_flag;
+};
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kPxThreads, 2)
+conv1x1_px_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                         const __grid_constant__ CUtensorMap tmWlo, const PxParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full[kPxStages], s_empty[kPxStages], s_aready[2], s_aempty[2], s_acc_full;
+  __shared__ uint32_t s_tmem_base;
+  __shared__ int s_fail;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tiles = (smem_addr(smem_raw) + 1023u) & ~1023u;
+  const uint8_t* tiles_ptr = smem_raw + (tiles - smem_addr(smem_raw));
+  const int co0 = blockIdx.x * kPxBN, px0 = blockIdx.y * kBM, img = blockIdx.z;
+  const int total_iters = (p.c_in + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPxStages; ++s) {
+      bar_init(smem_addr(&s_full[s]), 1);
+      bar_init(smem_addr(&s_empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      bar_init(smem_addr(&s_aready[a]), 4);   // one arrival per transform warp
+      bar_init(smem_addr(&s_aempty[a]), 1);
+    }
+    bar_init(smem_addr(&s_acc_full), 1);
+    s_fail = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_addr(&s_tmem_base)),
+                 "r"(kPxTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem_base;
+  const uint32_t acc_hi = tmem + 128u, acc_lo = tmem + 192u;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer: X tile (unswizzled), W and W_lo tiles (K-major, SW128) =====
+    for (int it = 0; it < total_iters; ++it) {
+      const int s = it % kPxStages;
+      const uint32_t ph = (it / kPxStages) & 1;
+      if (!bar_wait(smem_addr(&s_empty[s]), ph ^ 1)) {
+        s_fail = 1;
+        break;
+      }
+      const uint32_t full = smem_addr(&s_full[s]);
+      bar_expect_tx(full, kPxStageBytes);
+      const int k0 = it * kBK;
+      const uint32_t x_tile = tiles + s * kPxStageBytes, w_tile = x_tile + kPxXBytes, wlo_tile = w_tile + kPxWBytes;
+      tma_load_3d(x_tile, &tmX, px0, k0, img, full);
+      tma_load_3d(w_tile, &tmW, k0, co0, 0, full);
+      tma_load_3d(wlo_tile, &tmWlo, k0, co0, 0, full);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer: A from TMEM, three MMAs per K step =====
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kPxBN >> 3) << 17) |
+                           ((uint32_t)(kBM >> 4) << 24);      // f32 accumulate, tf32 x tf32, both K-major
+    bool failed = false;
+    for (int it = 0; it < total_iters; ++it) {
+      const int s = it % kPxStages, a = it & 1;
+      if (!bar_wait(smem_addr(&s_aready[a]), (it >> 1) & 1)) {
+        s_fail = 1;
+        failed = true;
+        break;
+      }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t w_tile = tiles + s * kPxStageBytes + kPxXBytes, wlo_tile = w_tile + kPxWBytes;
+      const uint32_t a_hi = tmem + (uint32_t)(a * 64), a_lo = a_hi + 32u;
+#pragma unroll
+      for (int j = 0; j < kBK / kUmmaK; ++j) {
+        const uint64_t db = desc_k_major(w_tile, j), dbl = desc_k_major(wlo_tile, j);
+        const uint32_t accumulate = (it > 0 || j > 0) ? 1u : 0u;
+        // the two small cross terms are summed apart from the leading term
+        mma_tf32_ts(acc_lo, a_lo + (uint32_t)(j * kUmmaK), db, idesc, accumulate);
+        mma_tf32_ts(acc_lo, a_hi + (uint32_t)(j * kUmmaK), dbl, idesc, 1u);
+        mma_tf32_ts(acc_hi, a_hi + (uint32_t)(j * kUmmaK), db, idesc, accumulate);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_addr(&s_empty[s]))
+                   : "memory");
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_addr(&s_aempty[a]))
+                   : "memory");
+    }
+    if (!failed)
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_addr(&s_acc_full))
+                   : "memory");
+  } else if (warp >= 4) {
+    // ===== transform warps: X tile -> {TF32 pattern, residual} -> TMEM; then the epilogue =====
+    const int quarter = warp - 4;                 // TMEM lane quarter this warp may access (warp % 4)
+    const int m = quarter * 32 + lane;            // pixel of this thread within the tile
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    bool ok = true;
+    for (int it = 0; it < total_iters && ok; ++it) {
+      const int s = it % kPxStages, a = it & 1;
+      ok = bar_wait(smem_addr(&s_full[s]), (it / kPxStages) & 1) &&
+           bar_wait(smem_addr(&s_aempty[a]), ((it >> 1) & 1) ^ 1);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) break;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const float* xs = reinterpret_cast<const float*>(tiles_ptr + s * kPxStageBytes) + m;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const float v = xs[k * kBM];
+        hi[k] = __float_as_uint(v);
+        lo[k] = __float_as_uint(tf32_residual(v));
+      }
+      tmem_st32(lane_base + (uint32_t)(a * 64), hi);
+      tmem_st32(lane_base + (uint32_t)(a * 64 + 32), lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&s_aready[a])) : "memory");
+    }
+    if (!ok) s_fail = 1;
+    // ----- epilogue: TMEM lane = pixel, columns = output channels -----
+    if (ok && total_iters > 0) {
+      ok = bar_wait(smem_addr(&s_acc_full), 0);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) s_fail = 1;
+    }
+    if (ok) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int px = px0 + m;
+      const bool valid = px < p.hw;
+      const long long plane = p.hw;
+      const long long base = ((long long)img * p.c_out + co0) * plane + px;
+#pragma unroll 1
+      for (int c = 0; c < kPxBN / 32; ++c) {
+        uint32_t r[32], r2[32];
+        if (total_iters > 0) {
+          tmem_ld32(lane_base + 128u + (uint32_t)(c * 32), r);
+          tmem_ld32(lane_base + 192u + (uint32_t)(c * 32), r2);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = r2[j] = 0u;
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int co = co0 + c * 32 + j;
+            if (co < p.c_out) {
+              float v = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+              if (p.bias) v += __ldg(p.bias + co);
+              const long long off = base + (long long)(c * 32 + j) * plane;
+              p.Y[off] = v;
+              if (p.Y2) p.Y2[off] = relu_keep_nan(v);
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (s_fail) {
+    if ((threadIdx.x & 31) == 0 && p.error_flag) atomicExch(p.error_flag, 1);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kPxTmemCols) : "memory");
+  }
+}
+
+// Unswizzled 3-D fp32 map (px, ci, img) with a [128 x 32 x 1] box for the pixel-major kernel.
+int make_map_px(CUtensorMap* map, const float* base, uint64_t hw, uint64_t c_in, uint64_t n_img);
+
+// im2col staging for the few-channel stem convolution (ResNet's 7x7 / stride 2 on 3 channels): the
+// tap-table kernel wants >= 16 input channels per tap, so here ALL taps and channels of an output
+// pixel are laid side by side,
+//     Xp[q][k],  q = (img * Ho + ho) * Wo + wo,  k = (c * kh + a) * kw + b  (zero for k >= C kh kw),
+// and the convolution is ONE tap with c_in = k_pad over the weight viewed as [c_out][C kh kw].
+// One warp per row: the (c, a, b) decomposition of a lane's columns is hoisted out of the row loop.
+constexpr int kIm2colMaxK = 256;
+
+__global__ void __launch_bounds__(256)
+im2col_kernel(const float* __restrict__ x, float* __restrict__ xp, int n_img, int C, int H, int W, int kh, int kw,
+              int stride, int pad, int Ho, int Wo, int k_pad) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int K = C * kh * kw;
+  int off[kIm2colMaxK / 32], da[kIm2colMaxK / 32], db[kIm2colMaxK / 32];
+#pragma unroll
+  for (int j = 0; j < kIm2colMaxK / 32; ++j) {
+    const int k = j * 32 + lane;
+    const int c = k / (kh * kw), r = k - c * (kh * kw);
+    da[j] = r / kw;
+    db[j] = r - da[j] * kw;
+    off[j] = k < K ? (c * H + da[j]) * W + db[j] : -1;
+  }
+  const long long rows = (long long)n_img * Ho * Wo;
+  for (long long q = warp; q < rows; q += n_warps) {
+    const int wo = (int)(q % Wo);
+    const int ho = (int)((q / Wo) % Ho);
+    const long long img = q / ((long long)Wo * Ho);
+    const int h0 = ho * stride - pad, w0 = wo * stride - pad;
+    const float* src = x + img * (long long)C * H * W + (long long)h0 * W + w0;
+    float* dst = xp + q * k_pad;
+#pragma unroll
+    for (int j = 0; j < kIm2colMaxK / 32; ++j) {
+      const int k = j * 32 + lane;
+      if (k < k_pad) {
+        float v = 0.f;
+        if (off[j] >= 0) {
+          const int h = h0 + da[j], w = w0 + db[j];
+          if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(src + off[j]);
+        }
+        dst[k] = v;
+      }
+    }
+  }
+}
+
 // ---- host: tensor maps ----------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -1073,6 +1353,30 @@ int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return DPL_E_UNSUPPORTED;
+  }
+  return 0;
+}
+
+int make_map_px(CUtensorMap* map, const float* base, uint64_t hw, uint64_t c_in, uint64_t n_img) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return DPL_E_UNSUPPORTED;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) || (hw & 3u)) {
+    set_error("activation not TMA-compatible: base 16-byte aligned and H*W a multiple of 4 required");
+    return DPL_E_UNSUPPORTED;
+  }
+  cuuint64_t dims[3] = {hw, c_in, n_img};
+  cuuint64_t strides[2] = {hw * 4, c_in * hw * 4};
+  cuuint32_t box[3] = {(cuuint32_t)kBM, (cuuint32_t)kBK, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (pixel-major map) failed with CUresult %d", (int)r);
     return DPL_E_UNSUPPORTED;
   }
   return 0;
@@ -1363,5 +1667,64 @@ extern "C" int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, con
   }
   conv_taps_tf32x3_kernel<<<grid, kGemm3Threads, smem, static_cast<cudaStream_t>(stream)>>>(tmX, tmW, tmWlo, p);
   DPL_LAUNCH_CHECK("conv_taps_tf32x3_kernel");
+  return 0;
+}
+
+// Pixel-major 1x1 convolution straight from / to NCHW (see conv1x1_px_tf32x3_kernel).
+//   d_x [n_img][c_in][hw], d_w [c_out][c_in] with residual d_w_lo, d_y [n_img][c_out][hw];
+//   hw and c_in multiples of 4 (TMA strides), else DPL_E_UNSUPPORTED.
+extern "C" int dpl_conv1x1_px_tf32x3(const float* d_x, const float* d_w, const float* d_w_lo, float* d_y, int n_img,
+                                     int c_in, int c_out, int hw, const float* d_bias, float* d_y_relu,
+                                     int* d_error_flag, void* stream) {
+  DPL_REQUIRE(d_x && d_w && d_w_lo && d_y, "null pointer");
+  DPL_REQUIRE(n_img > 0 && c_in > 0 && c_out > 0 && hw > 0, "empty problem");
+  DPL_REQUIRE(n_img <= 65535 && (hw + kBM - 1) / kBM <= 65535, "grid limit");
+  CUtensorMap tmX, tmW, tmWlo;
+  int st = make_map_px(&tmX, d_x, (uint64_t)hw, (uint64_t)c_in, (uint64_t)n_img);
+  if (st) return st;
+  st = make_map(&tmW, d_w, (uint64_t)c_in, (uint64_t)c_out, 1, (uint64_t)c_in, 0, (uint32_t)kPxBN, false);
+  if (!st) st = make_map(&tmWlo, d_w_lo, (uint64_t)c_in, (uint64_t)c_out, 1, (uint64_t)c_in, 0, (uint32_t)kPxBN, false);
+  if (st) return st;
+  PxParams p;
+  p.n_img = n_img;
+  p.c_in = c_in;
+  p.c_out = c_out;
+  p.hw = hw;
+  p.Y = d_y;
+  p.Y2 = d_y_relu;
+  p.bias = d_bias;
+  p.error_flag = d_error_flag;
+  // output-channel groups fastest: the CTAs that share an X tile run back to back (L2 reuse)
+  dim3 grid((unsigned)((c_out + kPxBN - 1) / kPxBN), (unsigned)((hw + kBM - 1) / kBM), (unsigned)n_img);
+  const size_t smem = (size_t)kPxStages * kPxStageBytes + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    int e = cuda_status(cudaFuncSetAttribute(conv1x1_px_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem),
+                        "cudaFuncSetAttribute(conv1x1_px_tf32x3_kernel)");
+    if (e) return e;
+    attr_done = true;
+  }
+  conv1x1_px_tf32x3_kernel<<<grid, kPxThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmX, tmW, tmWlo, p);
+  DPL_LAUNCH_CHECK("conv1x1_px_tf32x3_kernel");
+  return 0;
+}
+
+// im2col staging copy for the stem convolution (see im2col_kernel): d_xp [n_img * Ho * Wo][k_pad],
+// k_pad >= C * kh * kw, a multiple of 4 and <= 256.
+extern "C" int dpl_im2col_f32(const float* d_x, float* d_xp, int n_img, int channels, int H, int W, int kh, int kw,
+                              int stride, int pad, int Ho, int Wo, int k_pad, void* stream) {
+  DPL_REQUIRE(d_x && d_xp, "null pointer");
+  DPL_REQUIRE(n_img > 0 && channels > 0 && H > 0 && W > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0 && Ho > 0 &&
+                  Wo > 0,
+              "bad geometry");
+  DPL_REQUIRE(k_pad >= channels * kh * kw && k_pad <= kIm2colMaxK && (k_pad & 3) == 0, "k_pad out of range");
+  const long long rows = (long long)n_img * Ho * Wo;
+  long long blocks = (rows + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  im2col_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_xp, n_img, channels, H, W, kh,
+                                                                                 kw, stride, pad, Ho, Wo, k_pad);
+  DPL_LAUNCH_CHECK("im2col_kernel");
   return 0;
 }

@@ -15,15 +15,7 @@ namespace dpl {
 namespace {
 
 // ---- K5 ---------------------------------------------------------------------
-// Counter-based uniform in [0, 1): splitmix64 of (seed, element index). Not torch's
-// Philox stream — QDrop only needs an i.i.d. Bernoulli mask (brecq.py:169-170).
-__device__ __forceinline__ float uniform01(uint64_t seed, uint64_t i) {
-  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (i + 1);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (float)(z >> 40) * (1.0f / 16777216.0f);
-}
+__device__ __forceinline__ float uniform01(uint64_t seed, uint64_t i) { return hash_u01(seed, i); }
 
 __device__ __forceinline__ float fq1(float x, float s, float zp, float qlo, float qhi) {
   // round-half-even(x / s) + zp, saturate, dequantise (IEEE division, no reciprocal)
@@ -31,8 +23,39 @@ __device__ __forceinline__ float fq1(float x, float s, float zp, float qlo, floa
   q = fminf(fmaxf(q, qlo), qhi);
   return __fmul_rn(q - zp, s);
 }
+// same result through rint_div (r = RN(1 / s), fast == rint_div_ok(s, r))
+__device__ __forceinline__ float fq1r(float x, float s, float r, bool fast, float zp, float qlo, float qhi) {
+  float q = (fast ? rint_div(x, s, r) : rintf(__fdiv_rn(x, s))) + zp;
+  q = fminf(fmaxf(q, qlo), qhi);
+  return __fmul_rn(q - zp, s);
+}
 
-__global__ void __launch_bounds__(256)
+// Channel of element e for a per-channel tensor: (e / inner) % n_channels, in 32-bit arithmetic
+// when the tensor has fewer than 2^32 elements (a 64-bit divide costs ~10x a 32-bit one).
+__device__ __forceinline__ int channel_of(uint64_t e, uint64_t inner, int n_channels, bool small) {
+  if (small) return (int)(((uint32_t)e / (uint32_t)inner) % (uint32_t)n_channels);
+  return (int)((e / inner) % (uint64_t)n_channels);
+}
+
+__device__ __forceinline__ float4 fq4(float4 v, float s, float zp, float qlo, float qhi, bool drop,
+                                      float drop_prob, uint64_t seed, uint64_t e) {
+  float4 o;
+  const float r = __frcp_rn(s);
+  const bool fast = rint_div_ok(s, r);
+  o.x = fq1r(v.x, s, r, fast, zp, qlo, qhi);
+  o.y = fq1r(v.y, s, r, fast, zp, qlo, qhi);
+  o.z = fq1r(v.z, s, r, fast, zp, qlo, qhi);
+  o.w = fq1r(v.w, s, r, fast, zp, qlo, qhi);
+  if (drop) {
+    if (!(uniform01(seed, e) < drop_prob)) o.x = v.x;
+    if (!(uniform01(seed, e + 1) < drop_prob)) o.y = v.y;
+    if (!(uniform01(seed, e + 2) < drop_prob)) o.z = v.z;
+    if (!(uniform01(seed, e + 3) < drop_prob)) o.w = v.w;
+  }
+  return o;
+}
+
+__global__ void __launch_bounds__(256, 4)
 fakequant_kernel(const float* __restrict__ x, float* __restrict__ y, uint64_t n,
                  const float* __restrict__ scale, const int32_t* __restrict__ zero_point,
                  int n_channels, uint64_t inner, float qlo, float qhi, float drop_prob,
@@ -42,34 +65,30 @@ fakequant_kernel(const float* __restrict__ x, float* __restrict__ y, uint64_t n,
   const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0 &&
                    (n_channels == 1 || (inner & 3u) == 0);
   const bool drop = drop_prob < 1.0f;
+  const bool small = n < (1ull << 32);
   uint64_t done = 0;
   if (vec) {
     const uint64_t n4 = n >> 2;
     const float4* x4 = reinterpret_cast<const float4*>(x);
     float4* y4 = reinterpret_cast<float4*>(y);
-    for (uint64_t i = t; i < n4; i += stride) {
-      const int c = n_channels == 1 ? 0 : (int)(((i << 2) / inner) % (uint64_t)n_channels);
-      const float s = scale[c];
-      const float zp = zero_point ? (float)zero_point[c] : 0.f;
-      const float4 v = ldg_stream4(x4 + i);
-      float4 o;
-      o.x = fq1(v.x, s, zp, qlo, qhi);
-      o.y = fq1(v.y, s, zp, qlo, qhi);
-      o.z = fq1(v.z, s, zp, qlo, qhi);
-      o.w = fq1(v.w, s, zp, qlo, qhi);
-      if (drop) {
-        const uint64_t e = i << 2;
-        if (!(uniform01(seed, e) < drop_prob)) o.x = v.x;
-        if (!(uniform01(seed, e + 1) < drop_prob)) o.y = v.y;
-        if (!(uniform01(seed, e + 2) < drop_prob)) o.z = v.z;
-        if (!(uniform01(seed, e + 3) < drop_prob)) o.w = v.w;
+    for (uint64_t i = t; i < n4; i += 2 * stride) {   // two 16-byte loads in flight per thread
+      const bool two = i + stride < n4;
+      const float4 v0 = ldg_stream4(x4 + i);
+      const float4 v1 = two ? ldg_stream4(x4 + i + stride) : v0;
+      const int c0 = n_channels == 1 ? 0 : channel_of(i << 2, inner, n_channels, small);
+      const float s0 = scale[c0], z0 = zero_point ? (float)zero_point[c0] : 0.f;
+      stg_stream4(y4 + i, fq4(v0, s0, z0, qlo, qhi, drop, drop_prob, seed, i << 2));
+      if (two) {
+        const uint64_t j = i + stride;
+        const int c1 = n_channels == 1 ? 0 : channel_of(j << 2, inner, n_channels, small);
+        const float s1 = scale[c1], z1 = zero_point ? (float)zero_point[c1] : 0.f;
+        stg_stream4(y4 + j, fq4(v1, s1, z1, qlo, qhi, drop, drop_prob, seed, j << 2));
       }
-      y4[i] = o;
     }
     done = n4 << 2;
   }
   for (uint64_t i = done + t; i < n; i += stride) {
-    const int c = n_channels == 1 ? 0 : (int)((i / inner) % (uint64_t)n_channels);
+    const int c = n_channels == 1 ? 0 : channel_of(i, inner, n_channels, small);
     const float s = scale[c];
     const float zp = zero_point ? (float)zero_point[c] : 0.f;
     const float v = x[i];
@@ -80,10 +99,11 @@ fakequant_kernel(const float* __restrict__ x, float* __restrict__ y, uint64_t n,
 }
 
 // ---- K7a --------------------------------------------------------------------
-// One warp per (image, channel) row of `inner` elements; double atomics per channel.
+// One warp per (image, channel) row of `inner` elements (16-byte loads, four rows of lanes in
+// flight when the rows are aligned); double atomics per channel.
 __global__ void __launch_bounds__(256)
 channel_sumdiff_kernel(const float* __restrict__ a, const float* __restrict__ b, uint64_t n_rows,
-                       uint64_t channels, uint64_t inner, double* __restrict__ out) {
+                       uint64_t channels, uint64_t inner, double* __restrict__ out, int vec) {
   const int lane = threadIdx.x & 31;
   const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   for (uint64_t row = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < n_rows;
@@ -91,9 +111,28 @@ channel_sumdiff_kernel(const float* __restrict__ a, const float* __restrict__ b,
     const float* pa = a + row * inner;
     const float* pb = b + row * inner;
     double acc = 0.0;
+    uint64_t i0 = 0;
+    if (vec) {
+      const float4* a4 = reinterpret_cast<const float4*>(pa);
+      const float4* b4 = reinterpret_cast<const float4*>(pb);
+      const uint64_t n4 = inner >> 2;
+      for (uint64_t i = lane; i < n4; i += 128) {
+        float blk = 0.f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const uint64_t j = i + r * 32;
+          if (j < n4) {
+            const float4 u = ldg_stream4(a4 + j), v = ldg_stream4(b4 + j);
+            blk += (u.x - v.x) + (u.y - v.y) + (u.z - v.z) + (u.w - v.w);
+          }
+        }
+        acc += (double)blk;
+      }
+      i0 = n4 << 2;
+    }
     float blk = 0.f;
     int k = 0;
-    for (uint64_t i = lane; i < inner; i += 32) {
+    for (uint64_t i = i0 + lane; i < inner; i += 32) {
       blk += pa[i] - pb[i];
       if (++k == 16) {
         acc += (double)blk;
@@ -111,7 +150,7 @@ channel_sumdiff_kernel(const float* __restrict__ a, const float* __restrict__ b,
 constexpr uint32_t kCosChunk = 16384;
 __global__ void __launch_bounds__(256)
 cosine3_kernel(const float* __restrict__ a, const float* __restrict__ b, uint64_t seg_len,
-               uint64_t chunks_per_seg, double* __restrict__ out) {
+               uint64_t chunks_per_seg, double* __restrict__ out, int vec) {
   __shared__ double s_red[3][8];
   const uint64_t seg = blockIdx.x / chunks_per_seg;
   const uint64_t ch = blockIdx.x % chunks_per_seg;
@@ -119,11 +158,29 @@ cosine3_kernel(const float* __restrict__ a, const float* __restrict__ b, uint64_
   const float* pa = a + seg * seg_len;
   const float* pb = b + seg * seg_len;
   float ab = 0.f, aa = 0.f, bb = 0.f;
-  for (uint64_t i = e0 + threadIdx.x; i < e1; i += 256) {  // <= 64 elements per thread
-    const float u = pa[i], v = pb[i];
-    ab = fmaf(u, v, ab);
-    aa = fmaf(u, u, aa);
-    bb = fmaf(v, v, bb);
+  if (vec) {   // 16 float4 per thread and operand, all issued before use
+    const float4* a4 = reinterpret_cast<const float4*>(pa + e0);
+    const float4* b4 = reinterpret_cast<const float4*>(pb + e0);
+    const uint32_t n4 = (uint32_t)((e1 - e0) >> 2);
+#pragma unroll 4
+    for (uint32_t i = threadIdx.x; i < n4; i += 256) {
+      const float4 u = ldg_stream4(a4 + i), v = ldg_stream4(b4 + i);
+      ab = fmaf(u.x, v.x, ab); aa = fmaf(u.x, u.x, aa); bb = fmaf(v.x, v.x, bb);
+      ab = fmaf(u.y, v.y, ab); aa = fmaf(u.y, u.y, aa); bb = fmaf(v.y, v.y, bb);
+      ab = fmaf(u.z, v.z, ab); aa = fmaf(u.z, u.z, aa); bb = fmaf(v.z, v.z, bb);
+      ab = fmaf(u.w, v.w, ab); aa = fmaf(u.w, u.w, aa); bb = fmaf(v.w, v.w, bb);
+    }
+    for (uint64_t i = e0 + ((uint64_t)n4 << 2) + threadIdx.x; i < e1; i += 256) {
+      const float u = pa[i], v = pb[i];
+      ab = fmaf(u, v, ab); aa = fmaf(u, u, aa); bb = fmaf(v, v, bb);
+    }
+  } else {
+    for (uint64_t i = e0 + threadIdx.x; i < e1; i += 256) {  // <= 64 elements per thread
+      const float u = pa[i], v = pb[i];
+      ab = fmaf(u, v, ab);
+      aa = fmaf(u, u, aa);
+      bb = fmaf(v, v, bb);
+    }
   }
   double d0 = warp_sum((double)ab), d1 = warp_sum((double)aa), d2 = warp_sum((double)bb);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -161,7 +218,7 @@ adaround_init_kernel(const float* __restrict__ w, const float* __restrict__ scal
                      float* __restrict__ wfloor) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float s = scale[n_channels == 1 ? 0 : (i / inner) % (uint64_t)n_channels];
+    const float s = scale[n_channels == 1 ? 0 : channel_of(i, inner, n_channels, n < (1ull << 32))];
     const float q = __fdiv_rn(w[i], s);
     const float fl = floorf(q);
     const float rest = q - fl;
@@ -171,71 +228,128 @@ adaround_init_kernel(const float* __restrict__ w, const float* __restrict__ scal
   }
 }
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ float soft_w1(float wfl, float a, float s, float qmin, float qmax, int soft) {
+  const float r = soft ? rect_sigmoid(a) : (a >= 0.f ? 1.f : 0.f);
+  float q = wfl + r;
+  q = fminf(fmaxf(q, qmin), qmax);
+  return __fmul_rn(q, s);
+}
+
+// Weight-shaped tensors [n_channels][inner]: 16-byte accesses when a channel row is a multiple of four
+// elements (then the four lanes of a vector share their scale), channel index in 32-bit arithmetic.
+__global__ void __launch_bounds__(256, 4)
 adaround_weight_kernel(const float* __restrict__ wfloor, const float* __restrict__ alpha,
                        const float* __restrict__ scale, int n_channels, uint64_t inner, uint64_t n,
-                       float qmin, float qmax, int soft, float* __restrict__ wq) {
+                       float qmin, float qmax, int soft, float* __restrict__ wq, int vec) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float s = scale[n_channels == 1 ? 0 : (i / inner) % (uint64_t)n_channels];
-    const float a = alpha[i];
-    const float r = soft ? rect_sigmoid(a) : (a >= 0.f ? 1.f : 0.f);
-    float q = wfloor[i] + r;
-    q = fminf(fmaxf(q, qmin), qmax);
-    wq[i] = __fmul_rn(q, s);
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool small = n < (1ull << 32);
+  if (vec) {
+    const uint64_t n4 = n >> 2;
+    const float4* f4 = reinterpret_cast<const float4*>(wfloor);
+    const float4* a4 = reinterpret_cast<const float4*>(alpha);
+    float4* q4 = reinterpret_cast<float4*>(wq);
+    for (uint64_t i = tid; i < n4; i += stride) {
+      const float4 f = ldg_stream4(f4 + i), a = ldg_stream4(a4 + i);
+      const float s = scale[n_channels == 1 ? 0 : channel_of(i << 2, inner, n_channels, small)];
+      stg_stream4(q4 + i, make_float4(soft_w1(f.x, a.x, s, qmin, qmax, soft), soft_w1(f.y, a.y, s, qmin, qmax, soft),
+                                      soft_w1(f.z, a.z, s, qmin, qmax, soft), soft_w1(f.w, a.w, s, qmin, qmax, soft)));
+    }
+    return;   // vec implies n % 4 == 0
+  }
+  for (uint64_t i = tid; i < n; i += stride) {
+    const float s = scale[n_channels == 1 ? 0 : channel_of(i, inner, n_channels, small)];
+    wq[i] = soft_w1(wfloor[i], alpha[i], s, qmin, qmax, soft);
   }
 }
 
-__global__ void __launch_bounds__(256)
+struct StepCfg {
+  float qmin, qmax, beta, reg_alpha, lr, b1, b2, eps, bc1, bc2_sqrt, grad_scale;
+};
+
+// One element of the fused step: dL/d-alpha through the rectified sigmoid and the clamp, the
+// regulariser gradient, torch.optim.Adam's single-tensor update. Returns the regulariser term.
+__device__ __forceinline__ float step1(float gw, float wfl, float s, const StepCfg& c, float& a, float& mi,
+                                       float& vi) {
+  const float sg = sigmoidf_(a);
+  const float hraw = rect_sigmoid_raw(sg);
+  const float h = fminf(fmaxf(hraw, 0.f), 1.f);
+  // clamp(0,1) passes the gradient on the closed interval (torch.clamp backward)
+  const float dh = (hraw >= 0.f && hraw <= 1.f) ? (kZeta - kGamma) * sg * (1.f - sg) : 0.f;
+  // max(., qmin) / min(., qmax): pass where strictly inside, half on an exact tie
+  const float q = wfl + h;
+  float pass = 1.f;
+  if (q < c.qmin || q > c.qmax) pass = 0.f;
+  else if (q == c.qmin || q == c.qmax) pass = 0.5f;
+  float g = c.grad_scale * gw * s * pass * dh;
+  float reg = 0.f;
+  // regulariser: reg_alpha * sum(1 - |2h - 1|^beta)
+  if (c.beta > 0.f) {
+    const float u = fabsf(h - 0.5f) * 2.f;
+    const float sgn = (h > 0.5f) ? 1.f : ((h < 0.5f) ? -1.f : 0.f);
+    const float pw1 = powf(u, c.beta - 1.f);
+    g += -c.reg_alpha * c.beta * pw1 * 2.f * sgn * dh;
+    reg = c.reg_alpha * (1.f - pw1 * u);
+  }
+  // torch.optim.Adam (single-tensor path): lerp, addcmul, addcdiv
+  mi = mi + (g - mi) * (1.f - c.b1);
+  vi = vi * c.b2 + (1.f - c.b2) * g * g;
+  const float denom = sqrtf(vi) / c.bc2_sqrt + c.eps;
+  a = a - (c.lr / c.bc1) * (mi / denom);
+  return reg;
+}
+
+__global__ void __launch_bounds__(256, 4)
 adaround_step_kernel(const float* __restrict__ grad_w, const float* __restrict__ wfloor,
                      const float* __restrict__ scale, int n_channels, uint64_t inner, uint64_t n,
-                     float qmin, float qmax, float beta, float reg_alpha, float lr, float b1,
-                     float b2, float eps, float bc1, float bc2_sqrt, float grad_scale,
-                     float* __restrict__ alpha, float* __restrict__ m, float* __restrict__ v,
-                     double* __restrict__ reg_out, const float* __restrict__ sched) {
+                     StepCfg c, float* __restrict__ alpha, float* __restrict__ m, float* __restrict__ v,
+                     double* __restrict__ reg_out, const float* __restrict__ sched, int vec) {
   if (sched) {   // per-iteration scalars from device memory (CUDA-graph replay)
-    beta = sched[0];
-    bc1 = sched[1];
-    bc2_sqrt = sched[2];
+    c.beta = sched[0];
+    c.bc1 = sched[1];
+    c.bc2_sqrt = sched[2];
   }
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool small = n < (1ull << 32);
   double reg_acc = 0.0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float s = scale[n_channels == 1 ? 0 : (i / inner) % (uint64_t)n_channels];
-    const float a = alpha[i];
-    const float sg = sigmoidf_(a);
-    const float hraw = rect_sigmoid_raw(sg);
-    const float h = fminf(fmaxf(hraw, 0.f), 1.f);
-    // clamp(0,1) passes the gradient on the closed interval (torch.clamp backward)
-    const float dh = (hraw >= 0.f && hraw <= 1.f) ? (kZeta - kGamma) * sg * (1.f - sg) : 0.f;
-    // max(., qmin) / min(., qmax): pass where strictly inside, half on an exact tie
-    const float q = wfloor[i] + h;
-    float pass = 1.f;
-    if (q < qmin || q > qmax) pass = 0.f;
-    else if (q == qmin || q == qmax) pass = 0.5f;
-    float g = grad_scale * grad_w[i] * s * pass * dh;
-    // regulariser: reg_alpha * sum(1 - |2h - 1|^beta)
-    if (beta > 0.f) {
-      const float u = fabsf(h - 0.5f) * 2.f;
-      const float sgn = (h > 0.5f) ? 1.f : ((h < 0.5f) ? -1.f : 0.f);
-      const float pw1 = powf(u, beta - 1.f);
-      g += -reg_alpha * beta * pw1 * 2.f * sgn * dh;
-      reg_acc += (double)(reg_alpha * (1.f - pw1 * u));
+  if (vec) {
+    const uint64_t n4 = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(grad_w);
+    const float4* f4 = reinterpret_cast<const float4*>(wfloor);
+    float4* a4 = reinterpret_cast<float4*>(alpha);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    for (uint64_t i = tid; i < n4; i += stride) {
+      const float4 g = ldg_stream4(g4 + i), f = ldg_stream4(f4 + i);
+      float4 a = a4[i], mm = m4[i], vv = v4[i];
+      const float s = scale[n_channels == 1 ? 0 : channel_of(i << 2, inner, n_channels, small)];
+      float reg = step1(g.x, f.x, s, c, a.x, mm.x, vv.x);
+      reg += step1(g.y, f.y, s, c, a.y, mm.y, vv.y);
+      reg += step1(g.z, f.z, s, c, a.z, mm.z, vv.z);
+      reg += step1(g.w, f.w, s, c, a.w, mm.w, vv.w);
+      a4[i] = a;
+      m4[i] = mm;
+      v4[i] = vv;
+      reg_acc += (double)reg;
     }
-    // torch.optim.Adam (single-tensor path): lerp, addcmul, addcdiv
-    float mi = m[i], vi = v[i];
-    mi = mi + (g - mi) * (1.f - b1);
-    vi = vi * b2 + (1.f - b2) * g * g;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    alpha[i] = a - (lr / bc1) * (mi / denom);
-    m[i] = mi;
-    v[i] = vi;
+  } else {
+    for (uint64_t i = tid; i < n; i += stride) {
+      const float s = scale[n_channels == 1 ? 0 : channel_of(i, inner, n_channels, small)];
+      float a = alpha[i], mi = m[i], vi = v[i];
+      reg_acc += (double)step1(grad_w[i], wfloor[i], s, c, a, mi, vi);
+      alpha[i] = a;
+      m[i] = mi;
+      v[i] = vi;
+    }
   }
   if (reg_out) {
     reg_acc = warp_sum(reg_acc);
     if ((threadIdx.x & 31) == 0 && reg_acc != 0.0) atomicAdd(reg_out, reg_acc);
   }
 }
+
+inline bool al16q(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 inline unsigned ew_grid(uint64_t n, int per_thread) {
   uint64_t blocks = (n + 256ull * per_thread - 1) / (256ull * per_thread);
@@ -256,7 +370,7 @@ extern "C" int dpl_fakequant_f32(const float* d_x, float* d_y, uint64_t n, const
   DPL_REQUIRE(d_x && d_y && d_scale, "null pointer");
   DPL_REQUIRE(n_channels >= 1 && inner >= 1, "bad channel layout");
   if (n == 0) return 0;
-  fakequant_kernel<<<ew_grid(n, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  fakequant_kernel<<<stream_grid((n + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_x, d_y, n, d_scale, d_zero_point, n_channels, inner, (float)qlo, (float)qhi, drop_prob,
       seed);
   DPL_LAUNCH_CHECK("fakequant_kernel");
@@ -273,8 +387,10 @@ extern "C" int dpl_channel_sumdiff_f32(const float* d_a, const float* d_b, uint6
   uint64_t blocks = (rows + 7) / 8;
   const uint64_t cap = (uint64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
+  const int vec = ((reinterpret_cast<uintptr_t>(d_a) | reinterpret_cast<uintptr_t>(d_b)) & 15u) == 0 &&
+                  (inner & 3u) == 0;
   channel_sumdiff_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_a, d_b, rows, channels, inner, d_sum);
+      d_a, d_b, rows, channels, inner, d_sum, vec);
   DPL_LAUNCH_CHECK("channel_sumdiff_kernel");
   return 0;
 }
@@ -285,8 +401,11 @@ extern "C" int dpl_cosine3_f32(const float* d_a, const float* d_b, uint64_t n_se
   if (n_seg == 0 || seg_len == 0) return 0;
   const uint64_t cps = (seg_len + kCosChunk - 1) / kCosChunk;
   DPL_REQUIRE(n_seg * cps < (1ull << 31), "too many chunks");
+  // chunk starts are multiples of 16384 elements: rows are 16-byte aligned iff the bases and seg_len are
+  const int vec = ((reinterpret_cast<uintptr_t>(d_a) | reinterpret_cast<uintptr_t>(d_b)) & 15u) == 0 &&
+                  (seg_len & 3u) == 0;
   cosine3_kernel<<<(unsigned)(n_seg * cps), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_a, d_b, seg_len, cps, d_out);
+      d_a, d_b, seg_len, cps, d_out, vec);
   DPL_LAUNCH_CHECK("cosine3_kernel");
   return 0;
 }
@@ -310,8 +429,9 @@ extern "C" int dpl_adaround_weight_f32(const float* d_wfloor, const float* d_alp
   DPL_REQUIRE(d_wfloor && d_alpha && d_scale && d_wq, "null pointer");
   DPL_REQUIRE(n_channels >= 1 && inner >= 1, "bad channel layout");
   const uint64_t n = (uint64_t)n_channels * inner;
-  adaround_weight_kernel<<<ew_grid(n, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_wfloor, d_alpha, d_scale, n_channels, inner, n, qmin, qmax, soft, d_wq);
+  const int vec = al16q(d_wfloor) && al16q(d_alpha) && al16q(d_wq) && (inner & 3u) == 0;
+  adaround_weight_kernel<<<stream_grid(vec ? n / 4 : n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_wfloor, d_alpha, d_scale, n_channels, inner, n, qmin, qmax, soft, d_wq, vec);
   DPL_LAUNCH_CHECK("adaround_weight_kernel");
   return 0;
 }
@@ -328,9 +448,11 @@ extern "C" int dpl_adaround_step_f32(const float* d_grad_w, const float* d_wfloo
   // bias corrections in double like torch (Python floats), then float for the kernel
   const double bc1 = 1.0 - pow((double)b1, (double)step);
   const double bc2 = 1.0 - pow((double)b2, (double)step);
-  adaround_step_kernel<<<ew_grid(n, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_grad_w, d_wfloor, d_scale, n_channels, inner, n, qmin, qmax, beta, reg_alpha, lr, b1, b2,
-      eps, (float)bc1, (float)sqrt(bc2), grad_scale, d_alpha, d_m, d_v, d_reg, d_sched);
+  StepCfg c = {qmin, qmax, beta, reg_alpha, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), grad_scale};
+  const int vec = al16q(d_grad_w) && al16q(d_wfloor) && al16q(d_alpha) && al16q(d_m) && al16q(d_v) &&
+                  (inner & 3u) == 0;
+  adaround_step_kernel<<<stream_grid(vec ? n / 4 : n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_grad_w, d_wfloor, d_scale, n_channels, inner, n, c, d_alpha, d_m, d_v, d_reg, d_sched, vec);
   DPL_LAUNCH_CHECK("adaround_step_kernel");
   return 0;
 }

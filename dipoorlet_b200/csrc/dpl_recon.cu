@@ -18,13 +18,7 @@
 namespace dpl {
 namespace {
 
-__device__ __forceinline__ float u01(uint64_t seed, uint64_t i) {
-  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (i + 1);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (float)(z >> 40) * (1.0f / 16777216.0f);
-}
+__device__ __forceinline__ float u01(uint64_t seed, uint64_t i) { return hash_u01(seed, i); }
 
 // Per-iteration scalars live in device memory so that one captured CUDA graph can be replayed
 // for every iteration of the optimisation loop:
@@ -33,6 +27,7 @@ struct ActCfg {
   int relu;        // apply max(o, 0)
   int quant;       // apply fake-quant (per-tensor scale, symmetric [qmin, qmax])
   float scale, qmin, qmax;
+  float rscale;    // RN(1 / scale) for rint_div; 0 = use the plain IEEE division
   float prob;      // probability of taking the quantised value (1 = always, QDrop uses 0.5)
   uint64_t seed;
 };
@@ -46,65 +41,153 @@ __device__ __forceinline__ float act_fwd(float o, uint64_t i, const ActCfg& c, b
     y = fmaxf(o, 0.f);
   }
   if (c.quant) {
+    // branch-free: the quantised value is always formed, the mask selects (a divergent branch
+    // around the division cost more than the division)
     const bool take_q = (c.prob >= 1.0f) || (u01(c.seed, i) < c.prob);
-    if (take_q) {
-      float q = rintf(__fdiv_rn(y, c.scale));
-      q = fminf(fmaxf(q, c.qmin), c.qmax);
-      y = __fmul_rn(q, c.scale);
-      pass = false;
-    }
+    float q = c.rscale != 0.f ? rint_div(y, c.scale, c.rscale) : rintf(__fdiv_rn(y, c.scale));
+    q = fminf(fmaxf(q, c.qmin), c.qmax);
+    const float yq = __fmul_rn(q, c.scale);
+    y = take_q ? yq : y;
+    pass = pass && !take_q;
   }
   return y;
 }
 
-__global__ void __launch_bounds__(256)
+// All of them walk the tensor with 16-byte streaming loads / stores, two per operand in flight per
+// thread (the scalar versions with a 64-bit splitmix mask reached 31 - 63 % of the HBM peak on a
+// 205 MB blob; see profiles/ for these).
+__global__ void __launch_bounds__(256, 4)
 recon_act_kernel(const float* __restrict__ o, float* __restrict__ y, uint64_t n, ActCfg c,
-                 const unsigned long long* __restrict__ seed_ptr) {
+                 const unsigned long long* __restrict__ seed_ptr, int vec) {
   if (seed_ptr) c.seed = *seed_ptr;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t done = 0;
+  if (vec) {
+    const uint64_t n4 = n >> 2;
+    const float4* o4 = reinterpret_cast<const float4*>(o);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    for (uint64_t i = tid; i < n4; i += 2 * stride) {
+      const bool two = i + stride < n4;
+      const float4 a = ldg_stream4(o4 + i);
+      const float4 b = two ? ldg_stream4(o4 + i + stride) : a;
+      bool pass;
+      const uint64_t e = i << 2;
+      stg_stream4(y4 + i, make_float4(act_fwd(a.x, e, c, pass), act_fwd(a.y, e + 1, c, pass),
+                                      act_fwd(a.z, e + 2, c, pass), act_fwd(a.w, e + 3, c, pass)));
+      if (two) {
+        const uint64_t f = (i + stride) << 2;
+        stg_stream4(y4 + i + stride, make_float4(act_fwd(b.x, f, c, pass), act_fwd(b.y, f + 1, c, pass),
+                                                 act_fwd(b.z, f + 2, c, pass), act_fwd(b.w, f + 3, c, pass)));
+      }
+    }
+    done = n4 << 2;
+  }
+  for (uint64_t i = done + tid; i < n; i += stride) {
     bool pass;
     y[i] = act_fwd(o[i], i, c, pass);
   }
 }
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ float act_bwd1(float o, float gy, uint64_t i, const ActCfg& c) {
+  bool pass;
+  (void)act_fwd(o, i, c, pass);
+  return pass ? gy : 0.f;
+}
+
+__global__ void __launch_bounds__(256, 4)
 recon_act_bwd_kernel(const float* __restrict__ o, const float* __restrict__ gy,
                      float* __restrict__ go, uint64_t n, ActCfg c,
-                     const unsigned long long* __restrict__ seed_ptr) {
+                     const unsigned long long* __restrict__ seed_ptr, int vec) {
   if (seed_ptr) c.seed = *seed_ptr;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    bool pass;
-    (void)act_fwd(o[i], i, c, pass);
-    go[i] = pass ? gy[i] : 0.f;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t done = 0;
+  if (vec) {
+    const uint64_t n4 = n >> 2;
+    const float4* o4 = reinterpret_cast<const float4*>(o);
+    const float4* g4 = reinterpret_cast<const float4*>(gy);
+    float4* r4 = reinterpret_cast<float4*>(go);
+    for (uint64_t i = tid; i < n4; i += 2 * stride) {
+      const bool two = i + stride < n4;
+      const float4 a = ldg_stream4(o4 + i), ga = ldg_stream4(g4 + i);
+      const float4 b = two ? ldg_stream4(o4 + i + stride) : a;
+      const float4 gb = two ? ldg_stream4(g4 + i + stride) : ga;
+      const uint64_t e = i << 2;
+      stg_stream4(r4 + i, make_float4(act_bwd1(a.x, ga.x, e, c), act_bwd1(a.y, ga.y, e + 1, c),
+                                      act_bwd1(a.z, ga.z, e + 2, c), act_bwd1(a.w, ga.w, e + 3, c)));
+      if (two) {
+        const uint64_t f = (i + stride) << 2;
+        stg_stream4(r4 + i + stride, make_float4(act_bwd1(b.x, gb.x, f, c), act_bwd1(b.y, gb.y, f + 1, c),
+                                                 act_bwd1(b.z, gb.z, f + 2, c), act_bwd1(b.w, gb.w, f + 3, c)));
+      }
+    }
+    done = n4 << 2;
   }
+  for (uint64_t i = done + tid; i < n; i += stride) go[i] = act_bwd1(o[i], gy[i], i, c);
 }
 
 // loss = sum((act(o) - tgt)^2) * inv_count ; go = 2 * (act(o) - tgt) * inv_count * pass
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ float loss1(float o, float t, uint64_t i, const ActCfg& c, float inv_count,
+                                       float& blk) {
+  bool pass;
+  const float y = act_fwd(o, i, c, pass);
+  const float d = y - t;
+  blk = fmaf(d, d, blk);
+  return pass ? 2.f * d * inv_count : 0.f;
+}
+
+__global__ void __launch_bounds__(256, 4)
 recon_loss_kernel(const float* __restrict__ o, const float* __restrict__ tgt,
                   float* __restrict__ go, uint64_t n, ActCfg c, float inv_count,
-                  double* __restrict__ loss, const unsigned long long* __restrict__ seed_ptr) {
+                  double* __restrict__ loss, const unsigned long long* __restrict__ seed_ptr, int vec) {
   if (seed_ptr) c.seed = *seed_ptr;
   __shared__ double s_red[8];
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double acc = 0.0;
-  float blk = 0.f;
-  int k = 0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    bool pass;
-    const float y = act_fwd(o[i], i, c, pass);
-    const float d = y - tgt[i];
-    blk = fmaf(d, d, blk);
-    if (++k == 32) {
-      acc += (double)blk;
-      blk = 0.f;
-      k = 0;
+  uint64_t done = 0;
+  if (vec) {
+    const uint64_t n4 = n >> 2;
+    const float4* o4 = reinterpret_cast<const float4*>(o);
+    const float4* t4 = reinterpret_cast<const float4*>(tgt);
+    float4* r4 = reinterpret_cast<float4*>(go);
+    int k = 0;
+    float blk = 0.f;
+    for (uint64_t i = tid; i < n4; i += 2 * stride) {
+      const bool two = i + stride < n4;
+      const float4 a = ldg_stream4(o4 + i), ta = ldg_stream4(t4 + i);
+      const float4 b = two ? ldg_stream4(o4 + i + stride) : a;
+      const float4 tb = two ? ldg_stream4(t4 + i + stride) : ta;
+      const uint64_t e = i << 2;
+      float4 r;
+      r.x = loss1(a.x, ta.x, e, c, inv_count, blk);
+      r.y = loss1(a.y, ta.y, e + 1, c, inv_count, blk);
+      r.z = loss1(a.z, ta.z, e + 2, c, inv_count, blk);
+      r.w = loss1(a.w, ta.w, e + 3, c, inv_count, blk);
+      stg_stream4(r4 + i, r);
+      if (two) {
+        const uint64_t f = (i + stride) << 2;
+        r.x = loss1(b.x, tb.x, f, c, inv_count, blk);
+        r.y = loss1(b.y, tb.y, f + 1, c, inv_count, blk);
+        r.z = loss1(b.z, tb.z, f + 2, c, inv_count, blk);
+        r.w = loss1(b.w, tb.w, f + 3, c, inv_count, blk);
+        stg_stream4(r4 + i + stride, r);
+      }
+      if (++k == 4) {   // fold the float partial (<= 32 squares) into the double sum
+        acc += (double)blk;
+        blk = 0.f;
+        k = 0;
+      }
     }
-    go[i] = pass ? 2.f * d * inv_count : 0.f;
+    acc += (double)blk;
+    done = n4 << 2;
   }
-  acc += (double)blk;
+  {
+    float blk = 0.f;
+    for (uint64_t i = done + tid; i < n; i += stride) go[i] = loss1(o[i], tgt[i], i, c, inv_count, blk);
+    acc += (double)blk;
+  }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -138,21 +221,40 @@ __global__ void recon_schedule_kernel(int* __restrict__ iter, float* __restrict_
   *iter = t + 1;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 mix_drop_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
-                uint64_t n, float prob, uint64_t seed) {
+                uint64_t n, float prob, uint64_t seed, int vec) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    y[i] = (u01(seed, i) < prob) ? a[i] : b[i];
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t done = 0;
+  if (vec) {
+    const uint64_t n4 = n >> 2;
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    for (uint64_t i = tid; i < n4; i += 2 * stride) {
+      const bool two = i + stride < n4;
+      const float4 u0 = ldg_stream4(a4 + i), v0 = ldg_stream4(b4 + i);
+      const float4 u1 = two ? ldg_stream4(a4 + i + stride) : u0;
+      const float4 v1 = two ? ldg_stream4(b4 + i + stride) : v0;
+      const uint64_t e = i << 2;
+      stg_stream4(y4 + i, make_float4(u01(seed, e) < prob ? u0.x : v0.x, u01(seed, e + 1) < prob ? u0.y : v0.y,
+                                      u01(seed, e + 2) < prob ? u0.z : v0.z, u01(seed, e + 3) < prob ? u0.w : v0.w));
+      if (two) {
+        const uint64_t f = (i + stride) << 2;
+        stg_stream4(y4 + i + stride,
+                    make_float4(u01(seed, f) < prob ? u1.x : v1.x, u01(seed, f + 1) < prob ? u1.y : v1.y,
+                                u01(seed, f + 2) < prob ? u1.z : v1.z, u01(seed, f + 3) < prob ? u1.w : v1.w));
+      }
+    }
+    done = n4 << 2;
+  }
+  for (uint64_t i = done + tid; i < n; i += stride) y[i] = (u01(seed, i) < prob) ? a[i] : b[i];
 }
 
-inline unsigned grid_for(uint64_t n) {
-  uint64_t blocks = (n + 256ull * 4 - 1) / (256ull * 4);
-  const uint64_t cap = (uint64_t)sm_count() * 16;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  return (unsigned)blocks;
-}
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline unsigned grid_for(uint64_t n) { return stream_grid((n + 7) / 8); }
 
 inline ActCfg make_cfg(int relu, int quant, float scale, float qmin, float qmax, float prob,
                        uint64_t seed) {
@@ -160,6 +262,11 @@ inline ActCfg make_cfg(int relu, int quant, float scale, float qmin, float qmax,
   c.relu = relu;
   c.quant = quant;
   c.scale = scale;
+  {
+    const float r = 1.0f / scale;   // host division: correctly rounded
+    const float as = fabsf(scale), ar = fabsf(r);
+    c.rscale = (as >= 1.17549435e-38f && as < 1.0e37f && ar >= 1.17549435e-38f && ar < 1.0e37f) ? r : 0.f;
+  }
   c.qmin = qmin;
   c.qmax = qmax;
   c.prob = prob;
@@ -178,7 +285,7 @@ extern "C" int dpl_recon_act_f32(const float* d_o, float* d_y, uint64_t n, int r
   DPL_REQUIRE(d_o && d_y, "null pointer");
   if (n == 0) return 0;
   recon_act_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_o, d_y, n, make_cfg(relu, quant, scale, qmin, qmax, prob, seed), d_seed);
+      d_o, d_y, n, make_cfg(relu, quant, scale, qmin, qmax, prob, seed), d_seed, al16(d_o) && al16(d_y));
   DPL_LAUNCH_CHECK("recon_act_kernel");
   return 0;
 }
@@ -190,7 +297,8 @@ extern "C" int dpl_recon_act_bwd_f32(const float* d_o, const float* d_gy, float*
   DPL_REQUIRE(d_o && d_gy && d_go, "null pointer");
   if (n == 0) return 0;
   recon_act_bwd_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_o, d_gy, d_go, n, make_cfg(relu, quant, scale, qmin, qmax, prob, seed), d_seed);
+      d_o, d_gy, d_go, n, make_cfg(relu, quant, scale, qmin, qmax, prob, seed), d_seed,
+      al16(d_o) && al16(d_gy) && al16(d_go));
   DPL_LAUNCH_CHECK("recon_act_bwd_kernel");
   return 0;
 }
@@ -203,7 +311,7 @@ extern "C" int dpl_recon_loss_f32(const float* d_o, const float* d_tgt, float* d
   if (n == 0) return 0;
   recon_loss_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_o, d_tgt, d_go, n, make_cfg(relu, quant, scale, qmin, qmax, prob, seed), inv_count, d_loss,
-      d_seed);
+      d_seed, al16(d_o) && al16(d_tgt) && al16(d_go));
   DPL_LAUNCH_CHECK("recon_loss_kernel");
   return 0;
 }
@@ -212,8 +320,8 @@ extern "C" int dpl_mix_drop_f32(const float* d_a, const float* d_b, float* d_y, 
                                 float prob, uint64_t seed, void* stream) {
   DPL_REQUIRE(d_a && d_b && d_y, "null pointer");
   if (n == 0) return 0;
-  mix_drop_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_a, d_b, d_y, n, prob,
-                                                                             seed);
+  mix_drop_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_a, d_b, d_y, n, prob, seed, al16(d_a) && al16(d_b) && al16(d_y));
   DPL_LAUNCH_CHECK("mix_drop_kernel");
   return 0;
 }

@@ -995,9 +995,10 @@ extern "C" int dpl_segstats_f32(const dpl_blob* d_blobs, int n_blobs, uint64_t n
                                 uint64_t n_seg_tiles, float* d_min, float* d_max,
                                 double* d_abssum, uint64_t* d_nnz, float* d_blob_min,
                                 float* d_blob_max, void* d_scratch, size_t scratch_bytes,
-                                void* stream) {
+                                int ctas_per_sm, void* stream) {
   DPL_REQUIRE(d_blobs && n_blobs > 0, "empty blob table");
   DPL_REQUIRE(d_min && d_max, "null output");
+  DPL_REQUIRE(ctas_per_sm >= 0 && ctas_per_sm <= 8, "ctas_per_sm must be 0 (default) .. 8");
   if (n_segments == 0) return 0;
   if (scratch_bytes < dpl_segstats_scratch_bytes(n_seg_tiles) || !d_scratch) {
     set_error("dpl_segstats_f32: scratch too small (%zu < %zu)", scratch_bytes,
@@ -1013,7 +1014,9 @@ extern "C" int dpl_segstats_f32(const dpl_blob* d_blobs, int n_blobs, uint64_t n
   double* tsum = reinterpret_cast<double*>(base + 3 * a);
   if (n_seg_tiles > 0) {
     // 8 CTAs of 256 threads per SM; chunked tile ranges keep every CTA on one HBM stream
-    uint64_t grid = (uint64_t)sm_count() * 8;
+    // (fewer when the caller overlaps this pass with tensor-core kernels on another stream and
+    // wants it to fit beside their CTAs)
+    uint64_t grid = (uint64_t)sm_count() * (ctas_per_sm ? ctas_per_sm : 8);
     if (grid > n_seg_tiles) grid = n_seg_tiles;
     segstats_tiles_kernel<<<(unsigned)grid, kSegThreads, 0, st>>>(d_blobs, n_blobs, n_seg_tiles,
                                                                   tmin, tmax, tsum, tnnz);

@@ -48,10 +48,14 @@ class Engine:
         self.zero_points = {}
         self._w_lo = {}            # tf32 residuals of the 1x1 / Gemm weights (3xTF32 operand)
         self._w_taps = {}          # tap-major 3x3 filters + residuals
+        self._im2col = {}          # [co][C kh kw] stem filters + residuals
         self._pad_scratch = None   # zero-bordered input copy of the 3x3 convolution (grow-only)
         self.tc_conv3x3 = os.environ.get("DPL_ENGINE_CONV3X3", "1") != "0"
         self._tc_off = set()       # nodes the tensor-core tile could not address
         self.tensor_cores = os.environ.get("DPL_ENGINE_TCGEN05", "1") != "0"
+        # pixel-major TMEM-operand tile (dpl_conv1x1_px_tf32x3): correct and tested, but measured slower than
+        # the channel-major persistent tile on ResNet-50's shapes, so opt-in
+        self.conv1x1_px = os.environ.get("DPL_ENGINE_CONV1X1_PX", "0") == "1"
         self.native_ops = os.environ.get("DPL_ENGINE_NATIVE_OPS", "1") != "0"
         # Relu blob written by the Conv epilogue (second store stream). Measured on B200 at batch 64: the
         # Relu pass disappears (0.46 -> 0.07 ms) but the non-overlapped epilogues grow by more
@@ -62,6 +66,10 @@ class Engine:
         self.nodes = list(onnx_graph.model.graph.nodes)
         self._fused_q = set()
         self._relu_after = None    # Add node name -> the Relu node fused with it
+        # few-channel stem convolution through im2col staging + the single-tap tensor-core kernel: correct
+        # and tested, measured slower than cuDNN's fp32 kernel (1.05 vs 0.81 ms per 64 images: the staging
+        # copy is 475 MB), so opt-in until the gather moves into the kernel
+        self.stem_im2col = os.environ.get("DPL_ENGINE_STEM_IM2COL", "0") == "1"
 
     # ------------------------------------------------------------------ blob memory
     def _new(self, shape, like):
@@ -121,6 +129,7 @@ class Engine:
         for name in (names if names is not None else inits):
             self._w_lo.pop(name, None)
             self._w_taps.pop(name, None)
+            self._im2col.pop(name, None)
             arr = inits[name]
             if arr.dtype == np.float64:
                 arr = arr.astype(np.float32)
@@ -274,7 +283,8 @@ class Engine:
                     w2 = w.view(w.shape[0], w.shape[1])
                     out = self._new((x.shape[0], w.shape[0], x.shape[2], x.shape[3]), x)
                     r = self._relu_out(node, out, env)
-                    y = K.conv1x1_forward_x3(x, w2, self._residual(node.input[1], w2), b, out=out, out_relu=r)
+                    fwd = K.conv1x1_px_forward_x3 if self.conv1x1_px else K.conv1x1_forward_x3
+                    y = fwd(x, w2, self._residual(node.input[1], w2), b, out=out, out_relu=r)
                     self._publish_relu(node, r, env)
                     return [y]
                 except K.GemmUnsupported:
@@ -291,6 +301,29 @@ class Engine:
                     r = self._relu_out(node, out, env)
                     y = K.conv_taps_forward_x3(x, taps, taps_lo, taps_cfg[0], taps_cfg[1], b,
                                                scratch=self._pad_scratch, out=out, out_relu=r)
+                    self._publish_relu(node, r, env)
+                    return [y]
+                except K.GemmUnsupported:
+                    self._tc_off.add(node.name)
+            if (self.stem_im2col and self.tensor_cores and x.is_cuda and node.name not in self._tc_off and w.dim() == 4
+                    and x.is_contiguous() and a.get("group", 1) == 1 and list(dil) == [1, 1] and sym
+                    and lo[0] == lo[1] and stride[0] == stride[1] and x.shape[1] < 16
+                    and w.shape[1] * w.shape[2] * w.shape[3] <= 256):
+                try:   # few input channels (the stem): im2col staging + the single-tap tensor-core kernel
+                    prep = self._im2col.get(node.input[1]) if node.input[1] in self.params else None
+                    if prep is None:
+                        prep = K.conv_im2col_prepare(w)
+                        if node.input[1] in self.params:
+                            self._im2col[node.input[1]] = prep
+                    ho = (x.shape[2] + 2 * lo[0] - w.shape[2]) // stride[0] + 1
+                    wo = (x.shape[3] + 2 * lo[1] - w.shape[3]) // stride[1] + 1
+                    need = x.shape[0] * ho * wo * prep[2]
+                    if self._pad_scratch is None or self._pad_scratch.numel() < need:
+                        self._pad_scratch = torch.empty(need, dtype=torch.float32, device=x.device)
+                    out = self._new((x.shape[0], w.shape[0], ho, wo), x)
+                    r = self._relu_out(node, out, env)
+                    y = K.conv_im2col_forward_x3(x, prep, (int(w.shape[2]), int(w.shape[3])), int(stride[0]), int(lo[0]),
+                                                 b, out=out, scratch=self._pad_scratch, out_relu=r)
                     self._publish_relu(node, r, env)
                     return [y]
                 except K.GemmUnsupported:

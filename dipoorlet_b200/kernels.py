@@ -59,8 +59,14 @@ class BlobBatch:
         self.max_seg_len = max_seg
         self.n_blobs = n
         self.device = self.tensors[0].device if n else torch.device("cuda")
-        # small (8 KB for ResNet-50) synchronous-on-stream upload
-        self.table = torch.from_numpy(table.view(np.int64)).to(self.device, non_blocking=False)
+        # small (8 KB for ResNet-50) upload; through pinned memory it does not stall the host behind
+        # the kernels already queued on the stream
+        host = torch.from_numpy(table.view(np.int64))
+        if self.device.type == "cuda":
+            self._pinned = host.pin_memory()
+            self.table = self._pinned.to(self.device, non_blocking=True)
+        else:
+            self.table = host.to(self.device)
         self.elements = int(sum(int(t.numel()) for t in self.tensors))
 
     def seg_slices(self):
@@ -84,7 +90,7 @@ class Workspace:
 
 
 def segstats(batch, seg_min, seg_max, seg_abssum=None, seg_nnz=None, blob_min=None, blob_max=None,
-             workspace=None):
+             workspace=None, ctas_per_sm=0):
     """K1. seg_*: per-segment outputs (float32/float32/float64/int64[n_segments]);
     blob_min/blob_max: running per-blob extrema (float32[n_stats]), updated in place."""
     _need(seg_min, torch.float32, "seg_min")
@@ -99,7 +105,7 @@ def segstats(batch, seg_min, seg_max, seg_abssum=None, seg_nnz=None, blob_min=No
     check(lib().dpl_segstats_f32(batch.table.data_ptr(), batch.n_blobs, batch.n_segments,
                                  batch.n_seg_tiles, seg_min.data_ptr(), seg_max.data_ptr(),
                                  _lib._ptr(seg_abssum), _lib._ptr(seg_nnz), _lib._ptr(blob_min),
-                                 _lib._ptr(blob_max), ws.data_ptr(), ws.numel(), _stream()),
+                                 _lib._ptr(blob_max), ws.data_ptr(), ws.numel(), int(ctas_per_sm), _stream()),
           "dpl_segstats_f32")
     _count(2)
 
@@ -504,6 +510,29 @@ def conv1x1_forward_x3(x, w, w_lo, bias=None, relu=False, out=None, out_relu=Non
                        bias=bias, bias_mode=1 if bias is not None else 0, relu=relu, d_relu=out_relu)
 
 
+def conv1x1_px_forward_x3(x, w, w_lo, bias=None, out=None, out_relu=None):
+    """fp32-accurate 1x1 convolution, pixel-major tile (activations through TMEM), NCHW in / out."""
+    _need(x, torch.float32, "x")
+    _need(w, torch.float32, "w")
+    _need(w_lo, torch.float32, "w_lo")
+    n, ci, hh, ww = x.shape
+    co = w.shape[0]
+    o = torch.empty((n, co, hh, ww), dtype=torch.float32, device=x.device) if out is None else out
+    _need(o, torch.float32, "out")
+    _need(out_relu, torch.float32, "out_relu")
+    dev = x.device
+    flag = _gemm_err.get(dev)
+    if flag is None:
+        flag = _gemm_err[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = lib().dpl_conv1x1_px_tf32x3(x.data_ptr(), w.data_ptr(), w_lo.data_ptr(), o.data_ptr(), n, ci, co,
+                                     hh * ww, _lib._ptr(bias), _lib._ptr(out_relu), flag.data_ptr(), _stream())
+    if st == 10003:
+        raise GemmUnsupported(lib().dpl_last_error().decode("utf-8", "replace"))
+    check(st, "dpl_conv1x1_px_tf32x3")
+    _count()
+    return o
+
+
 def linear_forward_x3(x, w, w_lo=None, bias=None, out=None):
     """fp32-accurate Y = X W^T (+ bias): A = X (its residual is computed here, X is small),
     B = W is split inside the kernel, so `w_lo` is not needed."""
@@ -575,6 +604,48 @@ def conv_taps_forward_x3(x, taps, taps_lo, ksize, stride, bias=None, relu=False,
                                     y.data_ptr(), n, ci, co, plan.ho, plan.wo, plan.hp, plan.wp, plan.origin,
                                     len(plan.shifts), plan.c_shifts, _lib._ptr(bias), int(bool(relu)),
                                     _lib._ptr(out_relu), flag.data_ptr(), _stream())
+    if st == 10003:
+        raise GemmUnsupported(lib().dpl_last_error().decode("utf-8", "replace"))
+    check(st, "dpl_conv_taps_tf32x3")
+    _count()
+    return y
+
+
+def conv_im2col_prepare(w):
+    """[co][C][kh][kw] filter -> ([1][co][k_pad] row-major copy zero-padded to a multiple of 4, its
+    TF32 residual, k_pad) for conv_im2col_forward_x3 (once per weight)."""
+    co = w.shape[0]
+    k = w[0].numel()
+    k_pad = (k + 3) // 4 * 4
+    w2 = torch.zeros((1, co, k_pad), dtype=torch.float32, device=w.device)
+    w2[0, :, :k] = w.reshape(co, k)
+    return w2, tf32_residual(w2), k_pad
+
+
+def conv_im2col_forward_x3(x, prepared, kernel, stride, pad, bias=None, out=None, scratch=None, out_relu=None):
+    """fp32-accurate convolution with few input channels (the 7x7 / stride 2 stem): im2col staging
+    copy (dpl_im2col_f32), then the tap-table tensor-core kernel with a single tap."""
+    w2, w2_lo, k_pad = prepared
+    n, c, hh, ww = x.shape
+    kh, kw = kernel
+    co = w2.shape[1]
+    ho, wo = (hh + 2 * pad - kh) // stride + 1, (ww + 2 * pad - kw) // stride + 1
+    rows = n * ho * wo
+    need = rows * k_pad
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(need, dtype=torch.float32, device=x.device)
+    check(lib().dpl_im2col_f32(x.data_ptr(), scratch.data_ptr(), n, c, hh, ww, kh, kw, stride, pad, ho, wo, k_pad,
+                               _stream()), "dpl_im2col_f32")
+    _count()
+    y = torch.empty((n, co, ho, wo), dtype=torch.float32, device=x.device) if out is None else out
+    dev = x.device
+    flag = _gemm_err.get(dev)
+    if flag is None:
+        flag = _gemm_err[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    shifts = (ctypes.c_int * 1)(0)
+    st = lib().dpl_conv_taps_tf32x3(scratch.data_ptr(), rows, w2.data_ptr(), w2_lo.data_ptr(), y.data_ptr(), n, k_pad,
+                                    co, ho, wo, ho, wo, 0, 1, shifts, _lib._ptr(bias), 0, _lib._ptr(out_relu),
+                                    flag.data_ptr(), _stream())
     if st == 10003:
         raise GemmUnsupported(lib().dpl_last_error().decode("utf-8", "replace"))
     check(st, "dpl_conv_taps_tf32x3")

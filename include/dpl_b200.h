@@ -74,11 +74,13 @@ size_t dpl_segstats_scratch_bytes(uint64_t n_seg_tiles);
  * Also folds the batch into running per-blob extrema when d_blob_min/d_blob_max
  * (float32[n_stats], indexed by stat_index, caller-initialised to +inf/-inf) are
  * non-NULL — the device-resident equivalent of find_clip_val_minmax
- * (dipoorlet/tensor_cali/basic_algorithm.py:20-21). */
+ * (dipoorlet/tensor_cali/basic_algorithm.py:20-21).
+ * ctas_per_sm: 0 = the full-bandwidth grid (8 CTAs of 256 threads per SM); 1..8 = a smaller grid
+ * for a caller that runs this pass on a side stream underneath the forward's tensor-core kernels. */
 int dpl_segstats_f32(const dpl_blob* d_blobs, int n_blobs, uint64_t n_segments,
                      uint64_t n_seg_tiles, float* d_min, float* d_max, double* d_abssum,
                      uint64_t* d_nnz, float* d_blob_min, float* d_blob_max, void* d_scratch,
-                     size_t scratch_bytes, void* stream);
+                     size_t scratch_bytes, int ctas_per_sm, void* stream);
 
 /* data_max[b] = max(blob_max[b], -blob_min[b]) as float32 — forward_net.py:266-267. */
 int dpl_absmax_f32(const float* d_blob_min, const float* d_blob_max, float* d_data_max,
@@ -249,6 +251,25 @@ int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, const float* d
                          const float* d_w_taps_lo, float* d_y, int n_img, int c_in, int c_out, int Ho,
                          int Wo, int Hp, int Wp, int origin, int n_taps, const int* tap_shift,
                          const float* d_bias, int relu, float* d_y_relu, int* d_error_flag, void* stream);
+
+/* im2col staging for a convolution with very few input channels (ResNet's 7x7 / stride 2 stem, 3
+ * channels): d_xp[(img * Ho + ho) * Wo + wo][(c * kh + a) * kw + b] = X[img][c][ho * stride - pad + a]
+ * [wo * stride - pad + b] (0 outside, 0 for columns >= C kh kw); k_pad a multiple of 4, <= 256. The
+ * convolution is then dpl_conv_taps_tf32x3 with ONE tap, c_in = k_pad, Hp = Ho, Wp = Wo, origin 0 over
+ * the weight viewed as [c_out][C kh kw] (zero-padded to k_pad columns). */
+int dpl_im2col_f32(const float* d_x, float* d_xp, int n_img, int channels, int H, int W, int kh, int kw,
+                   int stride, int pad, int Ho, int Wo, int k_pad, void* stream);
+
+/* Pixel-major 1x1 convolution of the calibration forward, 3xTF32, straight from / to NCHW:
+ *   Y[img][co][px] = bias[co] + sum_ci W[co][ci] * X[img][ci][px]
+ * with the pixels on the TMEM lanes and the activations as the TMEM operand of tcgen05.mma (split
+ * into TF32 pattern + residual in registers), weights + host residual by TMA; 128 px x 64 co tiles,
+ * two CTAs per SM. d_y_relu (optional) also receives max(Y, 0). hw and c_in must be multiples of 4
+ * (TMA strides), otherwise DPL_E_UNSUPPORTED. Same reference operator as dpl_gemm_tf32x3
+ * (the Conv nodes ORT executes in dipoorlet/forward_net.py:200-216). */
+int dpl_conv1x1_px_tf32x3(const float* d_x, const float* d_w, const float* d_w_lo, float* d_y, int n_img,
+                          int c_in, int c_out, int hw, const float* d_bias, float* d_y_relu,
+                          int* d_error_flag, void* stream);
 
 /* Non-GEMM operators of the calibration forward — the Relu / Clip / Add / MaxPool /
  * GlobalAveragePool nodes onnxruntime executes per image in dipoorlet/forward_net.py:200-216 —

@@ -36,7 +36,7 @@ def _segs(batch):
 
 
 def segstats(batch, seg_min, seg_max, seg_abssum=None, seg_nnz=None, blob_min=None, blob_max=None,
-             workspace=None):
+             workspace=None, ctas_per_sm=0):
     for k, (b, x) in enumerate(_segs(batch)):
         seg_min[k], seg_max[k] = float(x.min()), float(x.max())
         if seg_abssum is not None:

@@ -103,6 +103,68 @@ def test_conv1x1_forward_3xtf32_is_fp32_accurate(dpl_built, dims):
     assert err <= 1e-5 * scale
 
 
+@pytest.mark.parametrize("dims", [(3, 64, 256, 56), (2, 96, 40, 28), (4, 1024, 256, 14), (1, 8, 136, 12),
+                                  (64, 64, 256, 28), (40, 512, 128, 14), (7, 256, 520, 10), (300, 32, 24, 6),
+                                  (2, 2048, 512, 8), (3, 36, 70, 30)])
+def test_conv1x1_pixel_major_3xtf32_is_fp32_accurate(dpl_built, dims):
+    """The pixel-major tile (activations as the TMEM operand): fp32 accuracy, ragged pixel / channel
+    tails (zero-filled by TMA, masked in the epilogue), and the fused Relu output."""
+    import torch
+    import torch.nn.functional as F
+    from dipoorlet_b200 import kernels as K
+    n, ci, co, hw = dims
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn((n, ci, hw, hw), device="cuda", generator=g)
+    w = torch.randn((co, ci), device="cuda", generator=g) * 0.1
+    b = torch.randn(co, device="cuda", generator=g)
+    out = torch.full((n, co, hw, hw), float("nan"), device="cuda")
+    out_relu = torch.full((n, co, hw, hw), float("nan"), device="cuda")
+    o = K.conv1x1_px_forward_x3(x, w, K.tf32_residual(w), b, out=out, out_relu=out_relu)
+    K.gemm_check_errors()
+    assert not torch.isnan(o).any()
+    assert torch.equal(out_relu, torch.relu(o))
+    want = torch.einsum("oc,nchw->nohw", w.double(), x.double()) + b.double().view(1, -1, 1, 1)
+    torch.backends.cudnn.allow_tf32 = False
+    ref32 = F.conv2d(x, w.view(co, ci, 1, 1), b)
+    err = (o.double() - want).abs().max().item()
+    err32 = (ref32.double() - want).abs().max().item()
+    scale = want.abs().max().item()
+    # one accumulator for the leading term: the tensor core's truncating accumulation shows beyond
+    # K = 1024 (5.8e-6 of the output scale at K = 2048, fp32 cuDNN: 1.7e-6)
+    assert err <= max((3 if ci <= 1024 else 5) * err32, 2e-6 * scale), (err, err32, scale)
+    assert err <= 1e-5 * scale
+    # no bias, no relu output
+    o2 = K.conv1x1_px_forward_x3(x, w, K.tf32_residual(w))
+    K.gemm_check_errors()
+    assert torch.allclose(o2, o - b.view(1, -1, 1, 1), rtol=0, atol=1e-5 * scale)
+
+
+@pytest.mark.parametrize("cfg", [(4, 3, 64, 64, 7, 2, 3), (2, 3, 16, 33, 7, 2, 3), (3, 1, 8, 20, 5, 1, 2),
+                                 (2, 4, 40, 18, 3, 2, 1)])
+def test_conv_im2col_stem_3xtf32_is_fp32_accurate(dpl_built, cfg):
+    """Few-channel convolution (ResNet's 7x7 / stride 2 stem) = im2col staging + the single-tap
+    tensor-core kernel: fp32 accuracy against float64, incl. ragged K (147 -> 148) and borders."""
+    import torch
+    import torch.nn.functional as F
+    from dipoorlet_b200 import kernels as K
+    n, ci, co, hw, k, stride, pad = cfg
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn((n, ci, hw, hw), device="cuda", generator=g)
+    w = torch.randn((co, ci, k, k), device="cuda", generator=g) * 0.1
+    b = torch.randn(co, device="cuda", generator=g)
+    prep = K.conv_im2col_prepare(w)
+    o = K.conv_im2col_forward_x3(x, prep, (k, k), stride, pad, b)
+    K.gemm_check_errors()
+    want = F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=pad)
+    assert o.shape == want.shape
+    torch.backends.cudnn.allow_tf32 = False
+    ref32 = F.conv2d(x, w, b, stride=stride, padding=pad)
+    err = (o.double() - want).abs().max().item()
+    err32 = (ref32.double() - want).abs().max().item()
+    scale = want.abs().max().item()
+    assert err <= max(3 * err32, 2e-6 * scale), (err, err32, scale)
+
+
 def test_linear_forward_3xtf32(dpl_built):
     import torch
     from dipoorlet_b200 import kernels as K

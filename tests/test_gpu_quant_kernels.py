@@ -43,6 +43,36 @@ def test_fakequant_matches_onnx_qdq(dpl_built, per_channel):
     assert np.array_equal(got, want)
 
 
+def test_fakequant_rounding_ties_bit_exact(dpl_built):
+    """The quotient is formed as x * RN(1/s) + one FMA correction, with the exact IEEE division only
+    next to a rounding tie: adversarial inputs on and one ulp around every tie, for awkward scales,
+    must round exactly like round_half_even(x / s) in IEEE fp32 (NumPy), and so must random data."""
+    import torch
+    from dipoorlet_b200 import kernels as K
+    rng = np.random.default_rng(5)
+    scales = np.concatenate([rng.random(40).astype(np.float32) * 0.2 + 1e-3,
+                             np.array([1 / 3, 0.1, 0.7, 1e-6, 3e4, np.float32(2 ** -10), 0.99999994], np.float32)])
+    n = np.arange(-140, 141, dtype=np.float32)
+    for s in scales:
+        ties = ((n + np.float32(0.5)) * s).astype(np.float32)
+        xs = [ties]
+        for k in range(1, 4):
+            up, dn = ties, ties
+            for _ in range(k):
+                up, dn = np.nextafter(up, np.float32(np.inf)), np.nextafter(dn, np.float32(-np.inf))
+            xs += [up.astype(np.float32), dn.astype(np.float32)]
+        x = np.concatenate(xs + [(rng.standard_normal(4096) * 60 * s).astype(np.float32),
+                                 np.array([np.inf, -np.inf, 0.0, -0.0, 3e38, -3e38], np.float32)])
+        q = np.rint(x / np.float32(s))                       # IEEE fp32 division, half-even
+        for lo, hi in ((-128, 127), (-127, 127)):
+            want = (np.clip(q, lo, hi) * np.float32(s)).astype(np.float32)
+            got = K.fakequant(torch.from_numpy(x).cuda(), torch.tensor([s], device="cuda"), None, lo, hi).cpu().numpy()
+            assert np.array_equal(got, want), (s, lo, np.flatnonzero(got != want)[:5])
+        # the reconstruction loop's epilogue shares the quotient (quant_acti, ada_quant_layer.py:28-36)
+        got = K.recon_act(torch.from_numpy(x).cuda(), False, (float(s), -127.0, 127.0)).cpu().numpy()
+        assert np.array_equal(got, (np.clip(q, -127, 127) * np.float32(s)).astype(np.float32)), s
+
+
 def test_channel_sumdiff_and_cosine(dpl_built):
     import torch
     from dipoorlet_b200 import kernels as K

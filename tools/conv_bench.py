@@ -25,7 +25,8 @@ def timed(fn, iters=10, warm=3):
 
 rows = []
 n = int(os.environ.get("CONV_BATCH", 64))
-for (ci, co, hw, k, stride) in [(64, 64, 56, 3, 1), (128, 128, 28, 3, 1), (256, 256, 14, 3, 1), (512, 512, 7, 3, 1),
+only_1x1 = os.environ.get("CONV_ONLY_1X1") == "1"
+for (ci, co, hw, k, stride) in [] if only_1x1 else [(64, 64, 56, 3, 1), (128, 128, 28, 3, 1), (256, 256, 14, 3, 1), (512, 512, 7, 3, 1),
                                 (128, 128, 56, 3, 2), (256, 256, 28, 3, 2), (512, 512, 14, 3, 2),
                                 (256, 512, 56, 1, 2), (512, 1024, 28, 1, 2), (1024, 2048, 14, 1, 2)]:
     x = torch.randn((n, ci, hw, hw), device="cuda")
@@ -68,6 +69,9 @@ for (ci, co, hw) in [(64, 256, 56), (256, 64, 56), (128, 512, 28), (512, 128, 28
     o = torch.empty((n, co, hw, hw), device="cuda")
     if (hw * hw) % 4 == 0:
         res["dpl_mn_ms"] = timed(lambda: K.conv1x1_forward_x3(x, w2, w_lo, b, out=o))
+        res["dpl_px_ms"] = timed(lambda: K.conv1x1_px_forward_x3(x, w2, w_lo, b, out=o))
+        K.gemm_check_errors()
+        res["px_max_abs_diff_vs_cudnn_fp32"] = (o - F.conv2d(x, w, b)).abs().max().item()
     taps, taps_lo = K.conv_taps_prepare(w)
     scratch = torch.empty(K.ConvPlan(n, hw, hw, 1, 1).total_rows * ci, device="cuda")
     res["dpl_staged_ms"] = timed(lambda: K.conv_taps_forward_x3(x, taps, taps_lo, 1, 1, b, out=o, scratch=scratch))
