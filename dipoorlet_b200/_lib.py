@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdpl_b200.so")
+# DPL_LIB: an alternative build of the same library (kernel-tuning experiments), else the in-tree one
+LIB_PATH = os.environ.get("DPL_LIB") or os.path.join(_HERE, "libdpl_b200.so")
 
 DPL_SEG_TILE = 8192
 DPL_FLAT_TILE = 8192

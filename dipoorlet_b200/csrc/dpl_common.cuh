@@ -86,20 +86,32 @@ __device__ __forceinline__ void stg_stream4(float4* p, float4 v) {
                : "memory");
 }
 
-// Counter-based uniform in [0, 1) keyed by (seed, element index): a 32-bit avalanche hash
-// (two multiply-xorshift rounds) of the index mixed with both halves of the seed. Not torch's
-// Philox stream - QDrop only needs an i.i.d. Bernoulli mask (brecq.py:169-170,
-// ada_quant_layer.py:28-36) that the backward pass can regenerate from the same (seed, index).
-// ~8 integer instructions per element (the 64-bit splitmix it replaces cost ~25).
-__device__ __forceinline__ float hash_u01(uint64_t seed, uint64_t i) {
-  uint32_t x = (uint32_t)i ^ (uint32_t)seed;
-  x += ((uint32_t)(i >> 32) ^ (uint32_t)(seed >> 32)) * 0x9E3779B9u;
+// Counter-based uniform in [0, 1) keyed by (seed, element index): a 32-bit avalanche hash (two
+// multiply-xorshift rounds) of the PAIR index i / 2 mixed with both halves of the seed; element i takes
+// the low or the high 16 bits. Not torch's Philox stream - QDrop only needs an i.i.d. Bernoulli mask
+// (brecq.py:169-170, ada_quant_layer.py:28-36) that the backward pass can regenerate from the same
+// (seed, index); 16 bits resolve the drop probability to 1.5e-5 (0.5 is exact). One hash serves two
+// elements: ~5 integer instructions per element (the 64-bit splitmix it replaces cost ~25).
+__device__ __forceinline__ uint32_t hash_pair(uint64_t seed, uint64_t j) {
+  uint32_t x = (uint32_t)j ^ (uint32_t)seed;
+  x += ((uint32_t)(j >> 32) ^ (uint32_t)(seed >> 32)) * 0x9E3779B9u;
   x ^= x >> 16;
   x *= 0x7FEB352Du;
   x ^= x >> 15;
   x *= 0x846CA68Bu;
   x ^= x >> 16;
-  return (float)(x >> 8) * (1.0f / 16777216.0f);
+  return x;
+}
+__device__ __forceinline__ float hash_u01(uint64_t seed, uint64_t i) {
+  const uint32_t h = hash_pair(seed, i >> 1);
+  return (float)((i & 1) ? (h >> 16) : (h & 0xFFFFu)) * (1.0f / 65536.0f);
+}
+// the four uniforms of elements e .. e + 3 (e a multiple of 4): two hashes
+__device__ __forceinline__ float4 hash_u01x4(uint64_t seed, uint64_t e) {
+  const uint32_t h0 = hash_pair(seed, e >> 1), h1 = hash_pair(seed, (e >> 1) + 1);
+  const float c = 1.0f / 65536.0f;
+  return make_float4((float)(h0 & 0xFFFFu) * c, (float)(h0 >> 16) * c, (float)(h1 & 0xFFFFu) * c,
+                     (float)(h1 >> 16) * c);
 }
 
 // rint(x / s) with the IEEE-correct quotient, without paying for a full division per element.
@@ -109,12 +121,38 @@ __device__ __forceinline__ float hash_u01(uint64_t seed, uint64_t i) {
 // the plain quotient's behaviour (inf -> saturates in the caller's clamp, NaN propagates).
 __device__ __forceinline__ float rint_div(float x, float s, float r) {
   const float q0 = __fmul_rn(x, r);
-  float q1 = __fmaf_rn(__fmaf_rn(-q0, s, x), r, q0);
-  if (!(fabsf(q0) < 3.0e38f)) q1 = q0;
+  const float q1 = __fmaf_rn(__fmaf_rn(-q0, s, x), r, q0);
   float t = rintf(q1);
-  if (fabsf(fabsf(q1 - t) - 0.5f) <= fmaxf(fabsf(q1), 1.f) * 1e-6f) t = rintf(__fdiv_rn(x, s));
+  // distance of q1 to the nearest tie against ~8 ulp of q1; written so that a NaN (inf * 0 in the
+  // correction step of a non-finite x) also takes the exact path
+  const float d = 0.5f - fabsf(q1 - t);
+  if (!(d > __fmaf_rn(fabsf(q1), 1e-6f, 1e-6f))) t = rintf(__fdiv_rn(x, s));
   return t;
 }
+// Four quotients at once: the fast evaluation is branch free, ONE (rarely taken) branch covers the
+// exact re-evaluation of the whole vector, so the four chains interleave.
+__device__ __forceinline__ float4 rint_div4(float4 x, float s, float r, bool fast) {
+  float4 t;
+  bool bad = !fast;
+#define DPL_RD1(c)                                                    \
+  {                                                                   \
+    const float q0 = __fmul_rn(x.c, r);                               \
+    const float q1 = __fmaf_rn(__fmaf_rn(-q0, s, x.c), r, q0);        \
+    t.c = rintf(q1);                                                  \
+    const float d = 0.5f - fabsf(q1 - t.c);                           \
+    bad |= !(d > __fmaf_rn(fabsf(q1), 1e-6f, 1e-6f));                 \
+  }
+  DPL_RD1(x) DPL_RD1(y) DPL_RD1(z) DPL_RD1(w)
+#undef DPL_RD1
+  if (bad) {
+    t.x = rintf(__fdiv_rn(x.x, s));
+    t.y = rintf(__fdiv_rn(x.y, s));
+    t.z = rintf(__fdiv_rn(x.z, s));
+    t.w = rintf(__fdiv_rn(x.w, s));
+  }
+  return t;
+}
+
 // True when rint_div may be used for this scale (normal, finite reciprocal); else use __fdiv_rn.
 __device__ __forceinline__ bool rint_div_ok(float s, float r) {
   return fabsf(s) >= 1.17549435e-38f && fabsf(s) < 1.0e37f && fabsf(r) >= 1.17549435e-38f && fabsf(r) < 1.0e37f;

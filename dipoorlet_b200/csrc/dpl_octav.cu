@@ -21,9 +21,17 @@
 namespace dpl {
 namespace {
 
-constexpr int kOctThreads = 512;
+// CTA shape (measured on B200, 3.4 GB batch, mixed data): 384 x 3 per SM 1.155 ms, 256 x 4 1.168 ms,
+// 256 x 6 1.199 ms, 512 x 2 1.227 ms, 1024 x 1 1.445 ms.
+#ifndef DPL_OCT_THREADS
+#define DPL_OCT_THREADS 384
+#endif
+#ifndef DPL_OCT_CTAS
+#define DPL_OCT_CTAS 3
+#endif
+constexpr int kOctThreads = DPL_OCT_THREADS;
 constexpr int kOctWarps = kOctThreads / 32;
-constexpr int kOctCtasPerSm = 2;
+constexpr int kOctCtasPerSm = DPL_OCT_CTAS;
 constexpr int kTailCap = 4096;   // survivors that fit in shared memory: one warp finishes alone
 
 struct PassAcc {

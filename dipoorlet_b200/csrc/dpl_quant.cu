@@ -37,20 +37,23 @@ __device__ __forceinline__ int channel_of(uint64_t e, uint64_t inner, int n_chan
   return (int)((e / inner) % (uint64_t)n_channels);
 }
 
-__device__ __forceinline__ float4 fq4(float4 v, float s, float zp, float qlo, float qhi, bool drop,
-                                      float drop_prob, uint64_t seed, uint64_t e) {
-  float4 o;
-  const float r = __frcp_rn(s);
-  const bool fast = rint_div_ok(s, r);
-  o.x = fq1r(v.x, s, r, fast, zp, qlo, qhi);
-  o.y = fq1r(v.y, s, r, fast, zp, qlo, qhi);
-  o.z = fq1r(v.z, s, r, fast, zp, qlo, qhi);
-  o.w = fq1r(v.w, s, r, fast, zp, qlo, qhi);
+__device__ __forceinline__ float fq_tail(float t, float s, float zp, float qlo, float qhi) {
+  float q = t + zp;
+  q = fminf(fmaxf(q, qlo), qhi);
+  return __fmul_rn(q - zp, s);
+}
+
+__device__ __forceinline__ float4 fq4(float4 v, float s, float r, bool fast, float zp, float qlo, float qhi,
+                                      bool drop, float drop_prob, uint64_t seed, uint64_t e) {
+  const float4 t = rint_div4(v, s, r, fast);
+  float4 o = make_float4(fq_tail(t.x, s, zp, qlo, qhi), fq_tail(t.y, s, zp, qlo, qhi), fq_tail(t.z, s, zp, qlo, qhi),
+                         fq_tail(t.w, s, zp, qlo, qhi));
   if (drop) {
-    if (!(uniform01(seed, e) < drop_prob)) o.x = v.x;
-    if (!(uniform01(seed, e + 1) < drop_prob)) o.y = v.y;
-    if (!(uniform01(seed, e + 2) < drop_prob)) o.z = v.z;
-    if (!(uniform01(seed, e + 3) < drop_prob)) o.w = v.w;
+    const float4 u = hash_u01x4(seed, e);
+    o.x = (u.x < drop_prob) ? o.x : v.x;
+    o.y = (u.y < drop_prob) ? o.y : v.y;
+    o.z = (u.z < drop_prob) ? o.z : v.z;
+    o.w = (u.w < drop_prob) ? o.w : v.w;
   }
   return o;
 }
@@ -66,23 +69,37 @@ fakequant_kernel(const float* __restrict__ x, float* __restrict__ y, uint64_t n,
                    (n_channels == 1 || (inner & 3u) == 0);
   const bool drop = drop_prob < 1.0f;
   const bool small = n < (1ull << 32);
+  const bool per_tensor = n_channels == 1;
+  // per-tensor: scale, its reciprocal and the zero point are loop invariants
+  float s0 = scale[0], r0 = __frcp_rn(s0), z0 = zero_point ? (float)zero_point[0] : 0.f;
+  bool f0 = rint_div_ok(s0, r0);
   uint64_t done = 0;
   if (vec) {
+    // CTA-contiguous tiles of 256 x R float4 (see dpl_eltwise.cu), R loads in flight per thread
+    constexpr int R = 4;
     const uint64_t n4 = n >> 2;
     const float4* x4 = reinterpret_cast<const float4*>(x);
     float4* y4 = reinterpret_cast<float4*>(y);
-    for (uint64_t i = t; i < n4; i += 2 * stride) {   // two 16-byte loads in flight per thread
-      const bool two = i + stride < n4;
-      const float4 v0 = ldg_stream4(x4 + i);
-      const float4 v1 = two ? ldg_stream4(x4 + i + stride) : v0;
-      const int c0 = n_channels == 1 ? 0 : channel_of(i << 2, inner, n_channels, small);
-      const float s0 = scale[c0], z0 = zero_point ? (float)zero_point[c0] : 0.f;
-      stg_stream4(y4 + i, fq4(v0, s0, z0, qlo, qhi, drop, drop_prob, seed, i << 2));
-      if (two) {
-        const uint64_t j = i + stride;
-        const int c1 = n_channels == 1 ? 0 : channel_of(j << 2, inner, n_channels, small);
-        const float s1 = scale[c1], z1 = zero_point ? (float)zero_point[c1] : 0.f;
-        stg_stream4(y4 + j, fq4(v1, s1, z1, qlo, qhi, drop, drop_prob, seed, j << 2));
+    const uint64_t tiles = (n4 + 256 * R - 1) / (256 * R);
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const uint64_t i0 = tile * (256 * R) + threadIdx.x;
+      float4 v[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (i0 + r * 256 < n4) v[r] = ldg_stream4(x4 + i0 + r * 256);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const uint64_t i = i0 + r * 256;
+        if (i < n4) {
+          if (!per_tensor) {
+            const int c0 = channel_of(i << 2, inner, n_channels, small);
+            s0 = scale[c0];
+            z0 = zero_point ? (float)zero_point[c0] : 0.f;
+            r0 = __frcp_rn(s0);
+            f0 = rint_div_ok(s0, r0);
+          }
+          stg_stream4(y4 + i, fq4(v[r], s0, r0, f0, z0, qlo, qhi, drop, drop_prob, seed, i << 2));
+        }
       }
     }
     done = n4 << 2;

@@ -56,6 +56,29 @@ __device__ __forceinline__ float act_fwd(float o, uint64_t i, const ActCfg& c, b
 // All of them walk the tensor with 16-byte streaming loads / stores, two per operand in flight per
 // thread (the scalar versions with a 64-bit splitmix mask reached 31 - 63 % of the HBM peak on a
 // 205 MB blob; see profiles/ for these).
+// Four elements at once (the quotients through rint_div4): y and the gradient-pass flags.
+__device__ __forceinline__ float4 act_fwd4(float4 o, uint64_t e, const ActCfg& c, bool (&pass)[4]) {
+  float4 y = o;
+  pass[0] = pass[1] = pass[2] = pass[3] = true;
+  if (c.relu) {
+    pass[0] = o.x > 0.f; pass[1] = o.y > 0.f; pass[2] = o.z > 0.f; pass[3] = o.w > 0.f;
+    y = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+  }
+  if (c.quant) {
+    const float4 t = rint_div4(y, c.scale, c.rscale, c.rscale != 0.f);
+    const bool all_q = c.prob >= 1.0f;
+    const float4 u = all_q ? make_float4(0.f, 0.f, 0.f, 0.f) : hash_u01x4(c.seed, e);
+    const bool q0 = all_q || (u.x < c.prob), q1 = all_q || (u.y < c.prob);
+    const bool q2 = all_q || (u.z < c.prob), q3 = all_q || (u.w < c.prob);
+    y.x = q0 ? __fmul_rn(fminf(fmaxf(t.x, c.qmin), c.qmax), c.scale) : y.x;
+    y.y = q1 ? __fmul_rn(fminf(fmaxf(t.y, c.qmin), c.qmax), c.scale) : y.y;
+    y.z = q2 ? __fmul_rn(fminf(fmaxf(t.z, c.qmin), c.qmax), c.scale) : y.z;
+    y.w = q3 ? __fmul_rn(fminf(fmaxf(t.w, c.qmin), c.qmax), c.scale) : y.w;
+    pass[0] = pass[0] && !q0; pass[1] = pass[1] && !q1; pass[2] = pass[2] && !q2; pass[3] = pass[3] && !q3;
+  }
+  return y;
+}
+
 __global__ void __launch_bounds__(256, 4)
 recon_act_kernel(const float* __restrict__ o, float* __restrict__ y, uint64_t n, ActCfg c,
                  const unsigned long long* __restrict__ seed_ptr, int vec) {
@@ -64,21 +87,23 @@ recon_act_kernel(const float* __restrict__ o, float* __restrict__ y, uint64_t n,
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t done = 0;
   if (vec) {
+    // CTA-contiguous tiles of 256 x R float4 (see dpl_eltwise.cu), R loads in flight per thread
+    constexpr int R = 4;
     const uint64_t n4 = n >> 2;
     const float4* o4 = reinterpret_cast<const float4*>(o);
     float4* y4 = reinterpret_cast<float4*>(y);
-    for (uint64_t i = tid; i < n4; i += 2 * stride) {
-      const bool two = i + stride < n4;
-      const float4 a = ldg_stream4(o4 + i);
-      const float4 b = two ? ldg_stream4(o4 + i + stride) : a;
-      bool pass;
-      const uint64_t e = i << 2;
-      stg_stream4(y4 + i, make_float4(act_fwd(a.x, e, c, pass), act_fwd(a.y, e + 1, c, pass),
-                                      act_fwd(a.z, e + 2, c, pass), act_fwd(a.w, e + 3, c, pass)));
-      if (two) {
-        const uint64_t f = (i + stride) << 2;
-        stg_stream4(y4 + i + stride, make_float4(act_fwd(b.x, f, c, pass), act_fwd(b.y, f + 1, c, pass),
-                                                 act_fwd(b.z, f + 2, c, pass), act_fwd(b.w, f + 3, c, pass)));
+    const uint64_t tiles = (n4 + 256 * R - 1) / (256 * R);
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const uint64_t i0 = tile * (256 * R) + threadIdx.x;
+      float4 v[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (i0 + r * 256 < n4) v[r] = ldg_stream4(o4 + i0 + r * 256);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const uint64_t i = i0 + r * 256;
+        bool pass[4];
+        if (i < n4) stg_stream4(y4 + i, act_fwd4(v[r], i << 2, c, pass));
       }
     }
     done = n4 << 2;
@@ -237,14 +262,13 @@ mix_drop_kernel(const float* __restrict__ a, const float* __restrict__ b, float*
       const float4 u0 = ldg_stream4(a4 + i), v0 = ldg_stream4(b4 + i);
       const float4 u1 = two ? ldg_stream4(a4 + i + stride) : u0;
       const float4 v1 = two ? ldg_stream4(b4 + i + stride) : v0;
-      const uint64_t e = i << 2;
-      stg_stream4(y4 + i, make_float4(u01(seed, e) < prob ? u0.x : v0.x, u01(seed, e + 1) < prob ? u0.y : v0.y,
-                                      u01(seed, e + 2) < prob ? u0.z : v0.z, u01(seed, e + 3) < prob ? u0.w : v0.w));
+      const float4 r0 = hash_u01x4(seed, i << 2);
+      stg_stream4(y4 + i, make_float4(r0.x < prob ? u0.x : v0.x, r0.y < prob ? u0.y : v0.y,
+                                      r0.z < prob ? u0.z : v0.z, r0.w < prob ? u0.w : v0.w));
       if (two) {
-        const uint64_t f = (i + stride) << 2;
-        stg_stream4(y4 + i + stride,
-                    make_float4(u01(seed, f) < prob ? u1.x : v1.x, u01(seed, f + 1) < prob ? u1.y : v1.y,
-                                u01(seed, f + 2) < prob ? u1.z : v1.z, u01(seed, f + 3) < prob ? u1.w : v1.w));
+        const float4 r1 = hash_u01x4(seed, (i + stride) << 2);
+        stg_stream4(y4 + i + stride, make_float4(r1.x < prob ? u1.x : v1.x, r1.y < prob ? u1.y : v1.y,
+                                                 r1.z < prob ? u1.z : v1.z, r1.w < prob ? u1.w : v1.w));
       }
     }
     done = n4 << 2;

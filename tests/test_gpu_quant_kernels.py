@@ -73,6 +73,36 @@ def test_fakequant_rounding_ties_bit_exact(dpl_built):
         assert np.array_equal(got, (np.clip(q, -127, 127) * np.float32(s)).astype(np.float32)), s
 
 
+def test_qdrop_mask_is_a_function_of_seed_and_index(dpl_built):
+    """The Bernoulli mask (brecq.py:169-170, ada_quant_layer.py:28-36) is regenerated, never stored:
+    the 16-byte and the scalar code paths, and the forward / backward kernels, must agree on it, its
+    mean must be the drop probability and different seeds must give different masks."""
+    import torch
+    from dipoorlet_b200 import kernels as K
+    n = 1 << 20
+    ones, zeros = torch.ones(n + 4, device="cuda"), torch.zeros(n + 4, device="cuda")
+    for p in (0.5, 0.3):
+        m_vec = K.mix_drop(ones[:n], zeros[:n], p, 11)
+        # misaligned operands take the scalar path over the same element indices
+        m_sca = K.mix_drop(ones[1:n + 1], zeros[1:n + 1], p, 11, out=torch.empty(n + 1, device="cuda")[1:])
+        assert torch.equal(m_vec, m_sca)
+        assert abs(m_vec.mean().item() - p) < 4 * (p * (1 - p) / n) ** 0.5
+        assert not torch.equal(m_vec, K.mix_drop(ones[:n], zeros[:n], p, 12))
+        # lag-1 correlation of neighbours (two elements share one hash word)
+        a, b = m_vec[:-1] - p, m_vec[1:] - p
+        assert abs((a * b).mean().item()) < 5e-3
+    o = torch.randn(n, device="cuda") * 3
+    gy = torch.ones(n, device="cuda")
+    y = K.recon_act(o, False, (0.05, -127.0, 127.0), prob=0.5, seed=5)
+    go = K.recon_act_bwd(o, gy, False, (0.05, -127.0, 127.0), prob=0.5, seed=5)
+    quantised = y != o                      # (a quantised value can equal o only on exact grid points)
+    assert torch.equal(go == 0, quantised | ((go == 0) & (y == o)))
+    assert (go[quantised] == 0).all() and abs(quantised.float().mean().item() - 0.5) < 0.01
+    loss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    gl = K.recon_loss(o, torch.zeros_like(o), 1.0, loss, False, (0.05, -127.0, 127.0), prob=0.5, seed=5)
+    assert torch.equal(gl == 0, go == 0) or ((gl == 0) != (go == 0)).float().mean().item() < 1e-3
+
+
 def test_channel_sumdiff_and_cosine(dpl_built):
     import torch
     from dipoorlet_b200 import kernels as K

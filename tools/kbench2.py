@@ -1,7 +1,8 @@
 """Microbenchmark of the streaming kernels around the statistics path (run on the GPU box):
 K5 fake-quant, K6 elementwise (soft weight, fused d-alpha + Adam, epilogues, loss, QDrop mix),
 K7 reductions and the forward engine's operators, each on buffers far larger than L2
-(a 64-image batch of a 256 x 56 x 56 blob = 205.5 MB per tensor), CUDA events, median of 10.
+(a 64-image batch of a 256 x 56 x 56 blob = 205.5 MB per tensor; the 126 MB L2 cannot hold an operand
+between launches), CUDA events around 8 back-to-back launches, median of 10.
 
     python tools/kbench2.py [--out gpurun_out/kbench2.json] [--quick]
 
@@ -20,6 +21,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dipoorlet_b200 import kernels as K  # noqa: E402
 
 
+REPS = 8   # launches per timed interval: these kernels run 60 - 400 us, an event pair adds a few us
+
+
 def timed(fn, iters=10, warm=3):
     for _ in range(warm):
         fn()
@@ -28,10 +32,11 @@ def timed(fn, iters=10, warm=3):
     for _ in range(iters):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        for _ in range(REPS):
+            fn()
         b.record()
         torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
+        ts.append(a.elapsed_time(b) / REPS)
     return float(np.median(ts)), float(np.min(ts))
 
 
