@@ -220,7 +220,7 @@ def run_ours(args):
         a = mk_args(source)
         sess = fwd.CalibrationSession(graph, a, engine=job.engine)
         job.engine = sess.engine
-        sess.run_minmax()
+        sess.run_minmax(per_image=False)     # what find_clip_val_hist runs (range over all images only)
         if timed_hist:
             sess.hist_events = hist_events
         sess.run_hist(BINS, args.hist_variant)
@@ -303,10 +303,12 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "images_per_gpu": n_img, "forward_batch": args.batch,
                    "l2": "inputs larger than L2: every timed kernel streams a %.1f GB batch of blobs "
                          "(126 MB L2)" % (4 * elems_per_img * args.batch / 1e9),
-                   "forward": ("1x1 / 3x3 / strided conv + Gemm: libdpl_b200 tcgen05 3xTF32 tiles (fp32-accurate); 7x7 stem conv, "
-                               "pooling, Relu, Add: torch/cuDNN fp32 stand-in (TF32 off)") if os.environ.get("DPL_ENGINE_TCGEN05", "1") != "0"
+                   "forward": ("libdpl_b200: 1x1 / 3x3 / strided conv + Gemm on tcgen05 3xTF32 tiles (fp32-accurate), Relu / Add / "
+                               "MaxPool / GlobalAveragePool streaming kernels with fused range statistics; 7x7 stem conv: "
+                               "torch/cuDNN fp32 stand-in (TF32 off)") if os.environ.get("DPL_ENGINE_TCGEN05", "1") != "0"
                    else "torch/cuDNN fp32 (TF32 off) stand-in producer",
-                   "statistics": "libdpl_b200.so (K1 segstats, K2 histogram variant 7, K3 percentile)",
+                   "statistics": "libdpl_b200.so (K1 segstats on the blobs the forward's kernels did not cover, K2 histogram "
+                                 "variant 7, K3 percentile)",
                    "resident_blobs": bool(resident_used["v"])},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_per_step,

@@ -21,6 +21,44 @@ __device__ __forceinline__ float clip1(float x, float lo, float hi) {
   return v > hi ? hi : v;
 }
 
+// Fused range statistics: every kernel here can fold the values it WRITES into the running per-blob
+// extrema (the blob-level result of K1, dpl_segstats_f32) - the producer already has the data in
+// registers, so pass 1 of a minmax / hist calibration needs no second read of these blobs.
+// NaN-free by contract (fminf / fmaxf skip NaN); -0 is canonicalised for the integer-ordered atomics.
+struct RangeAcc {
+  float lo, hi;
+  __device__ __forceinline__ RangeAcc() : lo(INFINITY), hi(-INFINITY) {}
+  __device__ __forceinline__ void add(float v) {
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+  __device__ __forceinline__ void add4(float4 v) {
+    lo = fminf(fminf(lo, v.x), fminf(fminf(v.y, v.z), v.w));
+    hi = fmaxf(fmaxf(hi, v.x), fmaxf(fmaxf(v.y, v.z), v.w));
+  }
+};
+
+// all threads of the CTA must call it (one barrier); s_lo / s_hi: shared float[32]
+__device__ __forceinline__ void range_flush(const RangeAcc& r, float* bmin, float* bmax, float* s_lo, float* s_hi) {
+  if (!bmin && !bmax) return;
+  const float lo = warp_min(r.lo), hi = warp_max(r.hi);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) {
+    s_lo[warp] = lo;
+    s_hi[warp] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l = s_lo[0], h = s_hi[0];
+    for (int w = 1; w < nw; ++w) {
+      l = fminf(l, s_lo[w]);
+      h = fmaxf(h, s_hi[w]);
+    }
+    if (bmin && l <= h) atomic_min_f32(bmin, l + 0.f);
+    if (bmax && l <= h) atomic_max_f32(bmax, h + 0.f);
+  }
+}
+
 __device__ __forceinline__ void st_stream4(float4* p, float4 v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
                "f"(v.z), "f"(v.w)
@@ -31,7 +69,10 @@ __device__ __forceinline__ void st_stream4(float4* p, float4 v) {
 // R = 4) per step, so its loads fall into a few DRAM pages instead of R pages a grid-stride apart
 // (grid-stride float4 loops measured 75 - 84 % of the HBM peak, tiles: see profiles/).
 __global__ void __launch_bounds__(kEltThreads, kEltCtasPerSm)
-clip_kernel(const float* __restrict__ x, float* __restrict__ y, uint64_t n, float lo, float hi, int vec) {
+clip_kernel(const float* __restrict__ x, float* __restrict__ y, uint64_t n, float lo, float hi, int vec,
+            float* __restrict__ bmin, float* __restrict__ bmax) {
+  __shared__ float s_lo[32], s_hi[32];
+  RangeAcc acc;
   uint64_t done = 0;
   if (vec) {
     constexpr int R = 4;
@@ -47,21 +88,32 @@ clip_kernel(const float* __restrict__ x, float* __restrict__ y, uint64_t n, floa
         if (i0 + r * kEltThreads < n4) v[r] = ldg_stream4(x4 + i0 + r * kEltThreads);
 #pragma unroll
       for (int r = 0; r < R; ++r)
-        if (i0 + r * kEltThreads < n4)
-          st_stream4(y4 + i0 + r * kEltThreads, make_float4(clip1(v[r].x, lo, hi), clip1(v[r].y, lo, hi),
-                                                            clip1(v[r].z, lo, hi), clip1(v[r].w, lo, hi)));
+        if (i0 + r * kEltThreads < n4) {
+          const float4 o = make_float4(clip1(v[r].x, lo, hi), clip1(v[r].y, lo, hi), clip1(v[r].z, lo, hi),
+                                       clip1(v[r].w, lo, hi));
+          st_stream4(y4 + i0 + r * kEltThreads, o);
+          acc.add4(o);
+        }
     }
     done = n4 << 2;
   }
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = done + tid; i < n; i += stride) y[i] = clip1(x[i], lo, hi);
+  for (uint64_t i = done + tid; i < n; i += stride) {
+    const float o = clip1(x[i], lo, hi);
+    y[i] = o;
+    acc.add(o);
+  }
+  range_flush(acc, bmin, bmax, s_lo, s_hi);
 }
 
 template <bool RELU>
 __global__ void __launch_bounds__(kEltThreads, 4)   // 64 registers: four vectors in flight, no spills
 add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
-           float* __restrict__ yr, uint64_t n, int vec) {
+           float* __restrict__ yr, uint64_t n, int vec, float* __restrict__ bmin, float* __restrict__ bmax,
+           float* __restrict__ rmin, float* __restrict__ rmax) {
+  __shared__ float s_lo[32], s_hi[32];
+  RangeAcc acc;   // of y; the Relu output's range follows from it: [max(lo, 0), max(hi, 0)]
   uint64_t done = 0;
   if (vec) {
     constexpr int R = 2;
@@ -85,6 +137,7 @@ add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __re
         if (i0 + r * kEltThreads < n4) {
           const float4 s = make_float4(u[r].x + w[r].x, u[r].y + w[r].y, u[r].z + w[r].z, u[r].w + w[r].w);
           st_stream4(y4 + i0 + r * kEltThreads, s);
+          acc.add4(s);
           if (RELU)
             st_stream4(r4 + i0 + r * kEltThreads,
                        make_float4(clip1(s.x, 0.f, INFINITY), clip1(s.y, 0.f, INFINITY), clip1(s.z, 0.f, INFINITY),
@@ -98,7 +151,18 @@ add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __re
   for (uint64_t i = done + tid; i < n; i += stride) {
     const float s = a[i] + b[i];
     y[i] = s;
+    acc.add(s);
     if (RELU) yr[i] = clip1(s, 0.f, INFINITY);
+  }
+  range_flush(acc, bmin, bmax, s_lo, s_hi);
+  if (RELU && (rmin || rmax)) {
+    RangeAcc racc;
+    if (acc.lo <= acc.hi) {
+      racc.lo = fmaxf(acc.lo, 0.f);
+      racc.hi = fmaxf(acc.hi, 0.f);
+    }
+    __syncthreads();
+    range_flush(racc, rmin, rmax, s_lo, s_hi);
   }
 }
 
@@ -109,48 +173,58 @@ add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __re
 template <int KH, int KW>
 __global__ void __launch_bounds__(256)
 maxpool2d_kernel(const float* __restrict__ x, float* __restrict__ y, uint32_t tiles_per_plane, int H, int W,
-                 int kh_rt, int kw_rt, int sh, int sw, int pt, int pl, int Ho, int Wo) {
+                 int kh_rt, int kw_rt, int sh, int sw, int pt, int pl, int Ho, int Wo, float* __restrict__ bmin,
+                 float* __restrict__ bmax) {
+  __shared__ float s_lo[32], s_hi[32];
+  RangeAcc acc;
   const int kh = KH ? KH : kh_rt, kw = KW ? KW : kw_rt;
   const uint32_t plane = blockIdx.x / tiles_per_plane;
   const uint32_t tile = blockIdx.x - plane * tiles_per_plane;
   const uint32_t idx = tile * 256u + threadIdx.x;
-  if (idx >= (uint32_t)(Ho * Wo)) return;
-  const int ho = (int)(idx / (uint32_t)Wo), wo = (int)(idx - (uint32_t)ho * (uint32_t)Wo);
-  const float* xp = x + (uint64_t)plane * (uint32_t)(H * W);
-  const int h0 = ho * sh - pt, w0 = wo * sw - pl;
-  float m = -INFINITY;
-  bool nan = false;
-  if (h0 >= 0 && w0 >= 0 && h0 + kh <= H && w0 + kw <= W) {
-    const float* p = xp + h0 * W + w0;
+  // no early exit: every thread of the CTA takes part in range_flush's shuffles and barrier
+  if (idx < (uint32_t)(Ho * Wo)) {
+    const int ho = (int)(idx / (uint32_t)Wo), wo = (int)(idx - (uint32_t)ho * (uint32_t)Wo);
+    const float* xp = x + (uint64_t)plane * (uint32_t)(H * W);
+    const int h0 = ho * sh - pt, w0 = wo * sw - pl;
+    float m = -INFINITY;
+    bool nan = false;
+    if (h0 >= 0 && w0 >= 0 && h0 + kh <= H && w0 + kw <= W) {
+      const float* p = xp + h0 * W + w0;
 #pragma unroll
-    for (int a = 0; a < kh; ++a) {
+      for (int a = 0; a < kh; ++a) {
 #pragma unroll
-      for (int c = 0; c < kw; ++c) {
-        const float v = __ldg(p + a * W + c);
-        nan |= (v != v);
-        m = fmaxf(m, v);
+        for (int c = 0; c < kw; ++c) {
+          const float v = __ldg(p + a * W + c);
+          nan |= (v != v);
+          m = fmaxf(m, v);
+        }
+      }
+    } else {
+      for (int a = 0; a < kh; ++a) {
+        const int h = h0 + a;
+        if (h < 0 || h >= H) continue;
+        const float* row = xp + h * W;
+        for (int c = 0; c < kw; ++c) {
+          const int w = w0 + c;
+          if (w < 0 || w >= W) continue;
+          const float v = __ldg(row + w);
+          nan |= (v != v);
+          m = fmaxf(m, v);
+        }
       }
     }
-  } else {
-    for (int a = 0; a < kh; ++a) {
-      const int h = h0 + a;
-      if (h < 0 || h >= H) continue;
-      const float* row = xp + h * W;
-      for (int c = 0; c < kw; ++c) {
-        const int w = w0 + c;
-        if (w < 0 || w >= W) continue;
-        const float v = __ldg(row + w);
-        nan |= (v != v);
-        m = fmaxf(m, v);
-      }
-    }
+    y[(uint64_t)plane * (uint32_t)(Ho * Wo) + idx] = nan ? NAN : m;
+    acc.add(m);
   }
-  y[(uint64_t)plane * (uint32_t)(Ho * Wo) + idx] = nan ? NAN : m;
+  range_flush(acc, bmin, bmax, s_lo, s_hi);
 }
 
 // One warp per (image, channel) plane: fp32 lane partials, shuffle tree, one division.
 __global__ void __launch_bounds__(256)
-global_avgpool_kernel(const float* __restrict__ x, float* __restrict__ y, uint64_t planes, uint64_t hw) {
+global_avgpool_kernel(const float* __restrict__ x, float* __restrict__ y, uint64_t planes, uint64_t hw,
+                      float* __restrict__ bmin, float* __restrict__ bmax) {
+  __shared__ float s_lo[32], s_hi[32];
+  RangeAcc racc;
   const int lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -159,8 +233,11 @@ global_avgpool_kernel(const float* __restrict__ x, float* __restrict__ y, uint64
     float acc = 0.f;
     for (uint64_t i = lane; i < hw; i += 32) acc += __ldg(xp + i);
     acc = warp_sum(acc);
-    if (lane == 0) y[p] = acc / (float)hw;
+    const float mean = acc / (float)hw;
+    if (lane == 0) y[p] = mean;
+    racc.add(mean);
   }
+  range_flush(racc, bmin, bmax, s_lo, s_hi);
 }
 
 inline unsigned elt_grid(uint64_t work_items) {
@@ -177,17 +254,19 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 using namespace dpl;
 
-extern "C" int dpl_clip_f32(const float* d_x, float* d_y, uint64_t n, float lo, float hi, void* stream) {
+extern "C" int dpl_clip_f32(const float* d_x, float* d_y, uint64_t n, float lo, float hi, float* d_blob_min,
+                            float* d_blob_max, void* stream) {
   DPL_REQUIRE(d_x && d_y, "null pointer");
   if (n == 0) return 0;
   const int vec = aligned16(d_x) && aligned16(d_y);
   clip_kernel<<<elt_grid(vec ? (n + 3) / 4 : n), kEltThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_x, d_y, n, lo, hi, vec);
+      d_x, d_y, n, lo, hi, vec, d_blob_min, d_blob_max);
   DPL_LAUNCH_CHECK("clip_kernel");
   return 0;
 }
 
 extern "C" int dpl_add_f32(const float* d_a, const float* d_b, float* d_y, float* d_y_relu, uint64_t n,
+                           float* d_blob_min, float* d_blob_max, float* d_relu_min, float* d_relu_max,
                            void* stream) {
   DPL_REQUIRE(d_a && d_b && d_y, "null pointer");
   if (n == 0) return 0;
@@ -195,16 +274,18 @@ extern "C" int dpl_add_f32(const float* d_a, const float* d_b, float* d_y, float
   const unsigned grid = elt_grid(vec ? (n + 3) / 4 : n);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (d_y_relu)
-    add_kernel<true><<<grid, kEltThreads, 0, st>>>(d_a, d_b, d_y, d_y_relu, n, vec);
+    add_kernel<true><<<grid, kEltThreads, 0, st>>>(d_a, d_b, d_y, d_y_relu, n, vec, d_blob_min, d_blob_max,
+                                                   d_relu_min, d_relu_max);
   else
-    add_kernel<false><<<grid, kEltThreads, 0, st>>>(d_a, d_b, d_y, nullptr, n, vec);
+    add_kernel<false><<<grid, kEltThreads, 0, st>>>(d_a, d_b, d_y, nullptr, n, vec, d_blob_min, d_blob_max,
+                                                    nullptr, nullptr);
   DPL_LAUNCH_CHECK("add_kernel");
   return 0;
 }
 
 extern "C" int dpl_maxpool2d_f32(const float* d_x, float* d_y, uint64_t planes, int H, int W, int kh,
                                  int kw, int sh, int sw, int pad_top, int pad_left, int Ho, int Wo,
-                                 void* stream) {
+                                 float* d_blob_min, float* d_blob_max, void* stream) {
   DPL_REQUIRE(d_x && d_y, "null pointer");
   DPL_REQUIRE(H > 0 && W > 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && Ho > 0 && Wo > 0, "bad geometry");
   if (planes == 0) return 0;
@@ -214,20 +295,21 @@ extern "C" int dpl_maxpool2d_f32(const float* d_x, float* d_y, uint64_t planes, 
   auto kern = (kh == 3 && kw == 3) ? maxpool2d_kernel<3, 3> : ((kh == 2 && kw == 2) ? maxpool2d_kernel<2, 2>
                                                                                       : maxpool2d_kernel<0, 0>);
   kern<<<(unsigned)(planes * tiles_per_plane), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_x, d_y, (uint32_t)tiles_per_plane, H, W, kh, kw, sh, sw, pad_top, pad_left, Ho, Wo);
+      d_x, d_y, (uint32_t)tiles_per_plane, H, W, kh, kw, sh, sw, pad_top, pad_left, Ho, Wo, d_blob_min, d_blob_max);
   DPL_LAUNCH_CHECK("maxpool2d_kernel");
   return 0;
 }
 
 extern "C" int dpl_global_avgpool_f32(const float* d_x, float* d_y, uint64_t planes, uint64_t hw,
-                                      void* stream) {
+                                      float* d_blob_min, float* d_blob_max, void* stream) {
   DPL_REQUIRE(d_x && d_y, "null pointer");
   DPL_REQUIRE(hw > 0, "empty plane");
   if (planes == 0) return 0;
   uint64_t grid = (planes * 32 + 255) / 256;
   const uint64_t cap = (uint64_t)sm_count() * 8;
   if (grid > cap) grid = cap;
-  global_avgpool_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_y, planes, hw);
+  global_avgpool_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_y, planes, hw,
+                                                                                       d_blob_min, d_blob_max);
   DPL_LAUNCH_CHECK("global_avgpool_kernel");
   return 0;
 }

@@ -34,6 +34,15 @@ def _sym_pads(pads, nd):
     return lo == hi, lo, hi
 
 
+class RangeSink:
+    """Where the forward's kernels fold min / max of the blobs they write (fused pass-1 statistics)."""
+
+    def __init__(self, blob_min, blob_max, names):
+        self.blob_min, self.blob_max = blob_min, blob_max
+        self.index = {n: i for i, n in enumerate(names)}
+        self.covered = set()
+
+
 class Engine:
     def __init__(self, onnx_graph, device=None, allow_tf32=False, _unit_test_cpu=False):
         self.g = onnx_graph
@@ -106,6 +115,14 @@ class Engine:
         if r is not None:
             env[self._fusable_relu(node).output[0]] = r
 
+    def _rng(self, name):
+        """Fused-statistics target of output `name` (None when no sink is attached)."""
+        st = getattr(self, "_stats", None)
+        if st is None or name not in st.index:
+            return None
+        st.covered.add(name)
+        return (st.blob_min, st.blob_max, st.index[name])
+
     def _native(self, x):
         return self.native_ops and torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 \
             and x.is_contiguous()
@@ -146,10 +163,13 @@ class Engine:
         outs = [o for n in self.nodes for o in n.output if o and o not in self.g.network_outputs]
         return list(self.g.network_inputs) + outs + list(self.g.network_outputs)
 
-    def run(self, feeds, want="all", start_after=None, cache=None):
+    def run(self, feeds, want="all", start_after=None, cache=None, stats=None):
         """feeds: name -> [B, ...] float32 CUDA tensor. Returns OrderedDict name -> tensor
         for `want` ('all' = every blob of blob_names(), or an iterable of names).
-        `cache` (dict) is consulted before computing a tensor and is not modified."""
+        `cache` (dict) is consulted before computing a tensor and is not modified.
+        `stats` (RangeSink): running per-blob min / max that the producing kernels update while they
+        write a blob; the names they covered are added to stats.covered."""
+        self._stats = stats
         torch.backends.cudnn.allow_tf32 = self.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = self.allow_tf32
         if os.environ.get("DPL_CUDNN_BENCHMARK"):   # let cuDNN time its fp32 algorithms per shape
@@ -185,6 +205,7 @@ class Engine:
                             if remaining[t] == 0 and t not in wanted and t not in feeds \
                                     and not (cache and t in cache):
                                 env.pop(t, None)
+        self._stats = None
         names = self.blob_names() if want_all else [w for w in want]
         return OrderedDict((n, env[n]) for n in names if n in env)
 
@@ -343,7 +364,7 @@ class Engine:
                                        a.get("dilations", [1] * nd))]
         if op == "Relu":
             if self._native(x):
-                return [K.clip(x, 0.0, float("inf"), out=self._new(x.shape, x))]
+                return [K.clip(x, 0.0, float("inf"), out=self._new(x.shape, x), rng=self._rng(node.output[0]))]
             return [torch.relu(x)]
         if op == "Clip":
             lo = a.get("min")
@@ -354,7 +375,7 @@ class Engine:
                 hi = float(self._host(node.input[2], env).reshape(-1)[0])
             if self._native(x):
                 return [K.clip(x, float("-inf") if lo is None else lo, float("inf") if hi is None else hi,
-                               out=self._new(x.shape, x))]
+                               out=self._new(x.shape, x), rng=self._rng(node.output[0]))]
             return [torch.clamp(x, lo, hi)]
         if op in ("MaxPool", "AveragePool"):
             nd = x.dim() - 2
@@ -371,7 +392,7 @@ class Engine:
                     return o
                 ho, wo = osz(x.shape[2], k[0], stride[0], lo[0], hi[0]), osz(x.shape[3], k[1], stride[1], lo[1], hi[1])
                 return [K.maxpool2d(x, k, stride, lo[0], lo[1], ho, wo,
-                                    out=self._new((x.shape[0], x.shape[1], ho, wo), x))]
+                                    out=self._new((x.shape[0], x.shape[1], ho, wo), x), rng=self._rng(node.output[0]))]
             if op == "MaxPool":
                 if not sym:
                     x = F.pad(x, [p for i in reversed(range(nd)) for p in (lo[i], hi[i])],
@@ -383,7 +404,8 @@ class Engine:
             return [F.avg_pool2d(x, k, stride, lo, ceil_mode, bool(a.get("count_include_pad", 0)))]
         if op == "GlobalAveragePool":
             if self._native(x) and x.dim() >= 3:
-                return [K.global_avgpool(x, out=self._new(tuple(x.shape[:2]) + (1,) * (x.dim() - 2), x))]
+                return [K.global_avgpool(x, out=self._new(tuple(x.shape[:2]) + (1,) * (x.dim() - 2), x),
+                                         rng=self._rng(node.output[0]))]
             return [x.mean(dim=tuple(range(2, x.dim())), keepdim=True)]
         if op in ("Add", "Sub", "Mul", "Div"):
             y = self._val(node.input[1], env)
@@ -392,10 +414,11 @@ class Engine:
                 if relu is not None and relu.output[0] not in env:
                     # the block's Add and the Relu behind it: both blobs from one read of the operands
                     r = self._new(x.shape, x)
-                    out = K.add(x, y, out=self._new(x.shape, x), out_relu=r)
+                    out = K.add(x, y, out=self._new(x.shape, x), out_relu=r, rng=self._rng(node.output[0]),
+                                rng_relu=self._rng(relu.output[0]))
                     env[relu.output[0]] = r
                     return [out]
-                return [K.add(x, y, out=self._new(x.shape, x))]
+                return [K.add(x, y, out=self._new(x.shape, x), rng=self._rng(node.output[0]))]
             return [{"Add": torch.add, "Sub": torch.sub, "Mul": torch.mul, "Div": torch.div}[op](x, y)]
         if op == "Flatten":
             ax = a.get("axis", 1)

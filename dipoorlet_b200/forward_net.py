@@ -20,7 +20,7 @@ import torch
 
 from . import dist_helper
 from . import kernels as K
-from .engine import Engine
+from .engine import Engine, RangeSink
 from .platform_settings import platform_setting_table
 from .utils import logger
 
@@ -151,6 +151,7 @@ class CalibrationSession:
         self.blob_min = torch.full((self.n_stats,), float("inf"), **f32)
         self.blob_max = torch.full((self.n_stats,), float("-inf"), **f32)
         self.seg_min = self.seg_max = self.seg_abssum = self.seg_nnz = self.seg_s = None
+        self.range_ready = False    # blob_min / blob_max hold this shard's range
         self.data_max = None
         self.counts = None
         # Resident mode: when the shard's blobs fit in HBM (1024 ResNet-50 images = 109 GB of
@@ -209,9 +210,10 @@ class CalibrationSession:
             feeds[name] = host.to(self.device, non_blocking=True)
         return feeds
 
-    def batches(self):
+    def batches(self, sink=None):
         """Forward batches with the NEXT batch's host->device copy issued on a side stream
-        while the current batch computes (the images come from pinned host memory)."""
+        while the current batch computes (the images come from pinned host memory).
+        `sink` (engine.RangeSink): fused range statistics, see run_minmax."""
         ranges = self._ranges()
         if self.device.type != "cuda" or not ranges:
             for b0, b1 in ranges:
@@ -264,19 +266,26 @@ class CalibrationSession:
                 nxt = prefetch((i + 1) & 1, ranges[i + 1])
             self.engine.arena = self.arena
             try:
-                blobs = self.engine.run(feeds, want="all")
+                blobs = self.engine.run(feeds, want="all", stats=sink)
             finally:
                 self.engine.arena = None
             yield b0 - self.st, b1 - self.st, K.BlobBatch([blobs[n] for n in self.names])
 
     # -- pass 1: min / max (+ moments for OCTAV) ------------------------------------
-    def run_minmax(self, moments=False, octav_k=None):
-        """Pass 1. With DPL_STATS_OVERLAP=1 the statistics kernels of batch i are enqueued on a side
+    def run_minmax(self, moments=False, octav_k=None, per_image=True):
+        """Pass 1. per_image=False (the minmax / hist calibrators, which only use the range over all
+        images, basic_algorithm.py:20-21,33-36): the forward's streaming kernels fold min / max of the
+        blobs they write into blob_min / blob_max themselves, and K1 reads only the remaining blobs
+        (convolution outputs, the input); seg_min / seg_max are then not produced. With DPL_STATS_OVERLAP=1 the statistics kernels of batch i are enqueued on a side
         stream and run underneath the forward of batch i + 1 (K1 on a reduced grid so that it fits beside
         the tensor-core CTAs). Measured on B200 (ResNet-50, batch 128): 6084 images/s with the overlap,
         6201 without - the forward's kernels lose more to the contention than the hidden K1 pass saves -
         so the default keeps everything on one stream."""
         n, dev = self.n_local, self.device
+        fused = (not per_image and not moments and octav_k is None and dev.type == "cuda"
+                 and os.environ.get("DPL_FUSED_RANGE", "1") != "0")
+        if fused:
+            return self._run_minmax_fused()
         self.seg_min = torch.empty((self.n_stats, n), dtype=torch.float32, device=dev)
         self.seg_max = torch.empty((self.n_stats, n), dtype=torch.float32, device=dev)
         if moments:
@@ -327,6 +336,25 @@ class CalibrationSession:
                 self.seg_s[:, lo:hi] = s.view(self.n_stats, b)
         del parts
         self.resident = keep
+        self.range_ready = True
+
+    def _run_minmax_fused(self):
+        dev = self.device
+        self.seg_min = self.seg_max = None
+        sink = RangeSink(self.blob_min, self.blob_max, self.names)
+        keep = [] if self.keep_resident else None
+        for lo, hi, batch in self.batches(sink=sink):
+            if keep is not None:
+                keep.append((lo, hi, batch))
+            rest = [i for i, nm in enumerate(self.names) if nm not in sink.covered]
+            if rest:
+                sub = K.BlobBatch([batch.tensors[i] for i in rest], stat_index=rest)
+                smin = torch.empty(sub.n_segments, dtype=torch.float32, device=dev)
+                smax = torch.empty_like(smin)
+                K.segstats(sub, smin, smax, None, None, self.blob_min, self.blob_max, self.ws)
+            del batch
+        self.resident = keep
+        self.range_ready = True
 
     # -- pass 2: histogram ------------------------------------------------------------
     def run_hist(self, bins, variant=0):
@@ -387,7 +415,7 @@ def forward_get_hist(onnx_graph, stats_min_max, args):
     summed over images (and ranks), in a one-element list so that the reference's
     `np.stack(hist).sum(0)` (basic_algorithm.py:38) is the identity (forward_net.py:240-281)."""
     sess = _session(onnx_graph, args)
-    if sess.seg_min is None:   # stats came from elsewhere (store_stats): seed the range
+    if not sess.range_ready:   # stats came from elsewhere (store_stats): seed the range
         mn = np.array([np.min(stats_min_max[n]["min"]) for n in sess.names], np.float32)
         mx = np.array([np.max(stats_min_max[n]["max"]) for n in sess.names], np.float32)
         sess.blob_min.copy_(torch.from_numpy(mn))

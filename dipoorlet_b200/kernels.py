@@ -291,18 +291,27 @@ def mix_drop(a, b, prob, seed, out=None):
 
 
 # ---- forward-engine operators (dpl_eltwise.cu) -------------------------------------------
-def clip(x, lo, hi, out=None):
-    """y = min(max(x, lo), hi); Relu is clip(x, 0, inf)."""
+def _rng(rng):
+    """(ptr to this blob's running min, ptr to its running max) or (0, 0): `rng` = (blob_min, blob_max,
+    index) with float32 CUDA arrays."""
+    if rng is None:
+        return 0, 0
+    bmin, bmax, idx = rng
+    return bmin.data_ptr() + 4 * int(idx), bmax.data_ptr() + 4 * int(idx)
+
+
+def clip(x, lo, hi, out=None, rng=None):
+    """y = min(max(x, lo), hi); Relu is clip(x, 0, inf). `rng`: fused range statistics of y."""
     _need(x, torch.float32, "x")
     y = torch.empty_like(x) if out is None else out
     _need(y, torch.float32, "out")
-    check(lib().dpl_clip_f32(x.data_ptr(), y.data_ptr(), x.numel(), float(lo), float(hi), _stream()),
+    check(lib().dpl_clip_f32(x.data_ptr(), y.data_ptr(), x.numel(), float(lo), float(hi), *_rng(rng), _stream()),
           "dpl_clip_f32")
     _count()
     return y
 
 
-def add(a, b, out=None, out_relu=None):
+def add(a, b, out=None, out_relu=None, rng=None, rng_relu=None):
     """y = a + b (same shape); with `out_relu` also max(y, 0) from the same pass."""
     _need(a, torch.float32, "a")
     _need(b, torch.float32, "b")
@@ -311,30 +320,30 @@ def add(a, b, out=None, out_relu=None):
     _need(y, torch.float32, "out")
     _need(out_relu, torch.float32, "out_relu")
     check(lib().dpl_add_f32(a.data_ptr(), b.data_ptr(), y.data_ptr(), _lib._ptr(out_relu), a.numel(),
-                            _stream()), "dpl_add_f32")
+                            *_rng(rng), *_rng(rng_relu), _stream()), "dpl_add_f32")
     _count()
     return y
 
 
-def maxpool2d(x, kernel, stride, pad_top, pad_left, ho, wo, out=None):
+def maxpool2d(x, kernel, stride, pad_top, pad_left, ho, wo, out=None, rng=None):
     _need(x, torch.float32, "x")
     n, c, h, w = x.shape
     y = torch.empty((n, c, ho, wo), dtype=torch.float32, device=x.device) if out is None else out
     _need(y, torch.float32, "out")
     check(lib().dpl_maxpool2d_f32(x.data_ptr(), y.data_ptr(), n * c, h, w, int(kernel[0]), int(kernel[1]),
                                   int(stride[0]), int(stride[1]), int(pad_top), int(pad_left), int(ho), int(wo),
-                                  _stream()), "dpl_maxpool2d_f32")
+                                  *_rng(rng), _stream()), "dpl_maxpool2d_f32")
     _count()
     return y
 
 
-def global_avgpool(x, out=None):
+def global_avgpool(x, out=None, rng=None):
     _need(x, torch.float32, "x")
     n, c = x.shape[0], x.shape[1]
     hw = x.numel() // max(n * c, 1)
     y = torch.empty((n, c) + (1,) * (x.dim() - 2), dtype=torch.float32, device=x.device) if out is None else out
     _need(y, torch.float32, "out")
-    check(lib().dpl_global_avgpool_f32(x.data_ptr(), y.data_ptr(), n * c, hw, _stream()),
+    check(lib().dpl_global_avgpool_f32(x.data_ptr(), y.data_ptr(), n * c, hw, *_rng(rng), _stream()),
           "dpl_global_avgpool_f32")
     _count()
     return y

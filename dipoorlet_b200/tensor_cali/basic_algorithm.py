@@ -23,8 +23,8 @@ def _global_images(sess, t):
 @tensor_cali_dispatcher.register('minmax')
 def find_clip_val_minmax(onnx_graph, args, **kwargs):
     """[min over images, max over images] per blob (basic_algorithm.py:13-22)."""
-    fwd.forward_get_minmax(onnx_graph, args)
-    sess = fwd._session(onnx_graph, args)
+    sess = fwd._session(onnx_graph, args, fresh=True)
+    sess.run_minmax(per_image=False)       # only the range over all images is used (:20-21)
     dist_helper.allreduce_minmax(sess.blob_min, sess.blob_max)
     lo, hi = sess.blob_min.cpu().numpy(), sess.blob_max.cpu().numpy()
     return {name: [lo[i], hi[i]] for i, name in enumerate(sess.names)}
@@ -47,7 +47,7 @@ def find_clip_val_hist(onnx_graph, args, store_stats=None, **kwargs):
         sess.counts = torch.from_numpy(np.stack([np.asarray(hist[n], dtype=np.int64) for n in sess.names])
                                        ).to(sess.device).contiguous()
     else:
-        sess.run_minmax()
+        sess.run_minmax(per_image=False)
         sess.run_hist(bins)
     clip, sel = sess.percentile_clip(bins, args.threshold)
     clip = clip.cpu().numpy()

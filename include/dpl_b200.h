@@ -278,13 +278,21 @@ int dpl_conv1x1_px_tf32x3(const float* d_x, const float* d_w, const float* d_w_l
  *   dpl_add_f32             y = a + b; when d_y_relu is non-NULL also y_relu = max(y, 0): the
  *                           residual Add and the Relu that follows it, both blobs from one read
  *   dpl_maxpool2d_f32       planes = n_img * channels planes of H x W -> Ho x Wo, padding = -inf
- *   dpl_global_avgpool_f32  y[plane] = mean of the plane's hw elements (fp32) */
-int dpl_clip_f32(const float* d_x, float* d_y, uint64_t n, float lo, float hi, void* stream);
+ *   dpl_global_avgpool_f32  y[plane] = mean of the plane's hw elements (fp32)
+ * Fused range statistics: d_blob_min / d_blob_max (optional, each ONE float32 = this blob's entry of
+ * the running per-blob extrema that dpl_segstats_f32 maintains, caller-initialised to +inf / -inf)
+ * receive min / max of the values the kernel writes, so a minmax / hist calibration does not read these
+ * blobs again for its range pass (find_clip_val_minmax, tensor_cali/basic_algorithm.py:20-21);
+ * d_relu_min / d_relu_max: the same for dpl_add_f32's second output. */
+int dpl_clip_f32(const float* d_x, float* d_y, uint64_t n, float lo, float hi, float* d_blob_min,
+                 float* d_blob_max, void* stream);
 int dpl_add_f32(const float* d_a, const float* d_b, float* d_y, float* d_y_relu, uint64_t n,
-                void* stream);
+                float* d_blob_min, float* d_blob_max, float* d_relu_min, float* d_relu_max, void* stream);
 int dpl_maxpool2d_f32(const float* d_x, float* d_y, uint64_t planes, int H, int W, int kh, int kw,
-                      int sh, int sw, int pad_top, int pad_left, int Ho, int Wo, void* stream);
-int dpl_global_avgpool_f32(const float* d_x, float* d_y, uint64_t planes, uint64_t hw, void* stream);
+                      int sh, int sw, int pad_top, int pad_left, int Ho, int Wo, float* d_blob_min,
+                      float* d_blob_max, void* stream);
+int dpl_global_avgpool_f32(const float* d_x, float* d_y, uint64_t planes, uint64_t hw, float* d_blob_min,
+                           float* d_blob_max, void* stream);
 
 #ifdef __cplusplus
 }

@@ -89,6 +89,46 @@ def test_engine_native_ops_match_library_ops(dpl_built, monkeypatch):
                 assert torch.equal(a[o], b[o]), o
 
 
+def test_fused_range_statistics_equal_k1(dpl_built):
+    """per_image=False: the streaming kernels fold min / max of the blobs they write and K1 reads only
+    the rest - the per-blob range (and so the histogram and the clip values) must be bit-identical to
+    the K1-over-everything pass; and the single-kernel form of every fused operator against torch."""
+    import torch
+    from dipoorlet_b200 import forward_net as fwd, kernels as K, workloads as W
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.graph import ONNXGraph
+    x = torch.randn((3, 5, 9, 11), device="cuda") * 2
+    y = torch.randn((3, 5, 9, 11), device="cuda")
+    lo = torch.full((4,), float("inf"), device="cuda")
+    hi = torch.full((4,), float("-inf"), device="cuda")
+    r = torch.empty_like(x)
+    K.clip(x, 0.0, 6.0, rng=(lo, hi, 0))
+    s = K.add(x, y, out_relu=r, rng=(lo, hi, 1), rng_relu=(lo, hi, 2))
+    g = K.global_avgpool(x, rng=(lo, hi, 3))
+    want = [torch.clamp(x, 0, 6), s, r, g]
+    assert lo.tolist() == [w.min().item() for w in want] and hi.tolist() == [w.max().item() for w in want]
+    mp = K.maxpool2d(x, (3, 3), (2, 2), 1, 1, 5, 6, rng=(lo, hi, 0))     # folds into the running entry
+    assert lo[0].item() == min(want[0].min().item(), mp.min().item())
+    assert hi[0].item() == max(want[0].max().item(), mp.max().item())
+
+    model = W.build_resnet50(blocks=[1, 1, 1, 1], width=16, num_classes=10, image=64)
+    graph = ONNXGraph(model, "/tmp/dpl_fused", "trt")
+    images = W.synthetic_images(10, (3, 64, 64), seed=6)
+    res = {}
+    for per_image in (True, False):
+        args = make_args(input_dir=fwd.ArrayInput({"input": images[:, 0]}), data_num=10, deploy="trt",
+                         act_quant="hist", output_dir="/tmp/dpl_fused", calib_bs=4)
+        sess = fwd.CalibrationSession(graph, args)
+        sess.run_minmax(per_image=per_image)
+        assert (sess.seg_min is None) == (not per_image)
+        sess.run_hist(2048)
+        clip, _ = sess.percentile_clip(2048, 0.99999)
+        res[per_image] = (sess.blob_min.cpu().numpy(), sess.blob_max.cpu().numpy(), sess.counts.cpu().numpy(),
+                          clip.cpu().numpy())
+    for u, v in zip(res[True], res[False]):
+        assert np.array_equal(u, v)
+
+
 def test_session_arena_resident_and_recompute_agree(dpl_built):
     """hist calibration with the blobs kept resident in one slab (pass 2 in place) and with the
     recycled one-batch slab (pass 2 recomputes): identical counts and clip values."""
