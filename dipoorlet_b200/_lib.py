@@ -75,12 +75,12 @@ SIGNATURES = {
     "dpl_gemm_tf32x3": (_c_int, [_c_vp, _c_vp, _c_int, ctypes.c_longlong, ctypes.c_longlong, _c_vp, _c_int,
                                  ctypes.c_longlong, ctypes.c_longlong, _c_vp, ctypes.c_longlong,
                                  ctypes.c_longlong, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_int,
-                                 _c_vp, _c_vp, _c_vp]),
+                                 _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "dpl_pad_plane_f32": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                    _c_int, _c_vp]),
     "dpl_conv_taps_tf32x3": (_c_int, [_c_vp, ctypes.c_longlong, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int,
                                       _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_int,
-                                      _c_vp, _c_vp, _c_vp]),
+                                      _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "dpl_mix_drop_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_u64, _c_flt, _c_u64, _c_vp]),
     "dpl_im2col_f32": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                 _c_int, _c_int, _c_int, _c_vp]),

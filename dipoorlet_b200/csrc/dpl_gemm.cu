@@ -51,7 +51,26 @@ struct GemmParams {
   int hi_alt;           // 3xTF32: alternate the leading term between two accumulators
   int* error_flag;
   float* D2;            // optional second output max(D, 0) with D's layout (the Relu blob behind a Conv)
+  float* bmin;          // optional fused range statistics of D (one float each, see dpl_clip_f32)
+  float* bmax;
+  float* rmin;          // ... and of D2
+  float* rmax;
 };
+
+// Warp-level fold of a thread's range of written values into the running per-blob extrema.
+// All 32 lanes must call it. NaN-free by contract; -0 canonicalised for the integer-ordered atomics.
+__device__ __forceinline__ void warp_range_flush(float lo, float hi, float* bmin, float* bmax, float* rmin,
+                                                 float* rmax) {
+  if (!bmin && !bmax && !rmin && !rmax) return;
+  lo = warp_min(lo);
+  hi = warp_max(hi);
+  if ((threadIdx.x & 31) == 0 && lo <= hi) {
+    if (bmin) atomic_min_f32(bmin, lo + 0.f);
+    if (bmax) atomic_max_f32(bmax, hi + 0.f);
+    if (rmin) atomic_min_f32(rmin, fmaxf(lo, 0.f));
+    if (rmax) atomic_max_f32(rmax, fmaxf(hi, 0.f));
+  }
+}
 
 __device__ __forceinline__ float relu_keep_nan(float v) { return v < 0.f ? 0.f : v; }
 
@@ -484,6 +503,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int m = m0 + warp * 32 + lane;
       float* drow = p.D + (long long)z * p.d_batch_stride + (long long)m * p.ldd;
       const float bias_m = (p.bias_mode == 1 && m < p.M) ? p.bias[m] : 0.f;
+      float rlo = INFINITY, rhi = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < kBN / 32; ++c) {
         uint32_t r[32], r1[32], r2[32];
@@ -502,6 +522,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             v[j] = (acc + __uint_as_float(r2[j])) + bias_m;
             if (p.bias_mode == 2 && nc + j < p.N) v[j] += p.bias[nc + j];
             if (p.relu) v[j] = fmaxf(v[j], 0.f);
+            if (nc + j < p.N) {
+              rlo = fminf(rlo, v[j]);
+              rhi = fmaxf(rhi, v[j]);
+            }
           }
           float* dst = drow + nc;
           float* dst2 = p.D2 ? p.D2 + (drow - p.D) + nc : nullptr;
@@ -526,6 +550,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
         }
       }
+      warp_range_flush(rlo, rhi, p.bmin, p.bmax, p.rmin, p.rmax);
     }
   }
   if (!ok || s_fail) {
@@ -698,6 +723,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
     // ===== epilogue warps (TMEM lane quarter = warp - 8) =====
     const int wq = warp - 8;
     int t = 0;
+    float rlo = INFINITY, rhi = -INFINITY;   // range of everything this thread stores, flushed once
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
       const int mt = tile % m_tiles, nt = (tile / m_tiles) % n_tiles, z = tile / (m_tiles * n_tiles);
       const int m0 = mt * kBM, n0 = nt * kBN;
@@ -734,6 +760,10 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
           for (int j = 0; j < 32; ++j) {
             v[j] = (__uint_as_float(r[j]) + __uint_as_float(r2[j])) + bias_m;
             if (p.relu) v[j] = fmaxf(v[j], 0.f);
+            if (nc + j < p.N) {
+              rlo = fminf(rlo, v[j]);
+              rhi = fmaxf(rhi, v[j]);
+            }
           }
           float* dst = drow + nc;
           float* dst2 = p.D2 ? p.D2 + (drow - p.D) + nc : nullptr;
@@ -759,6 +789,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         }
       }
     }
+    warp_range_flush(rlo, rhi, p.bmin, p.bmax, p.rmin, p.rmax);
   }
   __syncwarp();
   if (s_fail) {
@@ -811,6 +842,7 @@ struct ConvParams {
   int relu;
   int* error_flag;
   float* Y2;            // optional second output max(Y, 0) (the Relu blob behind the Conv)
+  float *bmin, *bmax, *rmin, *rmax;   // optional fused range statistics of Y / Y2
 };
 
 __global__ void __launch_bounds__(kGemm3Threads, 1)
@@ -959,6 +991,7 @@ conv_taps_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         out_base = (((long long)img * p.c_out) * p.H + ho) * p.W + wo;
       }
       const long long ch_stride = (long long)p.H * p.W;
+      float rlo = INFINITY, rhi = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < p.bn / 32; ++c) {
         uint32_t r[32], r1[32], r2[32];
@@ -980,10 +1013,13 @@ conv_taps_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
               if (p.relu) v = fmaxf(v, 0.f);
               dst[(long long)j * ch_stride] = v;
               if (p.Y2) p.Y2[(dst - p.Y) + (long long)j * ch_stride] = relu_keep_nan(v);
+              rlo = fminf(rlo, v);
+              rhi = fmaxf(rhi, v);
             }
           }
         }
       }
+      warp_range_flush(rlo, rhi, p.bmin, p.bmax, p.rmin, p.rmax);
     }
   }
   if (!ok || s_fail) {
@@ -1445,6 +1481,7 @@ extern "C" int dpl_gemm_tf32(const float* d_a, int a_major, long long lda, long 
   p.relu = relu;
   p.error_flag = d_error_flag;
   p.D2 = nullptr;
+  p.bmin = p.bmax = p.rmin = p.rmax = nullptr;
   unsigned gz;
   if (fold_batch) {
     if (split_k < 1) split_k = 1;
@@ -1502,7 +1539,8 @@ extern "C" int dpl_gemm_tf32x3(const float* d_a, const float* d_a_lo, int a_majo
                                long long a_batch_stride, const float* d_b, int b_major, long long ldb,
                                long long b_batch_stride, float* d_d, long long ldd, long long d_batch_stride,
                                int M, int N, int K, int batch, const float* d_bias, int bias_mode, int relu,
-                               float* d_d_relu, int* d_error_flag, void* stream) {
+                               float* d_d_relu, float* d_blob_min, float* d_blob_max, float* d_relu_min,
+                               float* d_relu_max, int* d_error_flag, void* stream) {
   DPL_REQUIRE(d_a && d_a_lo && d_b && d_d, "null pointer");
   DPL_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "empty problem");
   DPL_REQUIRE(bias_mode == 0 || d_bias, "bias_mode without bias");
@@ -1540,6 +1578,10 @@ extern "C" int dpl_gemm_tf32x3(const float* d_a, const float* d_a_lo, int a_majo
   p.hi_alt = x3_hi_alt();
   p.error_flag = d_error_flag;
   p.D2 = d_d_relu;
+  p.bmin = d_blob_min;
+  p.bmax = d_blob_max;
+  p.rmin = d_relu_min;
+  p.rmax = d_relu_max;
   dim3 grid((M + kBM - 1) / kBM, (N + kBN - 1) / kBN, (unsigned)batch);
   const size_t smem = (size_t)kStages3 * kStageBytes3 + 1024;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1612,7 +1654,8 @@ extern "C" int dpl_pad_plane_f32(const float* d_x, float* d_xp, int n_img, int c
 extern "C" int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, const float* d_w_taps,
                                     const float* d_w_taps_lo, float* d_y, int n_img, int c_in, int c_out, int Ho,
                                     int Wo, int Hp, int Wp, int origin, int n_taps, const int* tap_shift,
-                                    const float* d_bias, int relu, float* d_y_relu, int* d_error_flag,
+                                    const float* d_bias, int relu, float* d_y_relu, float* d_blob_min,
+                                    float* d_blob_max, float* d_relu_min, float* d_relu_max, int* d_error_flag,
                                     void* stream) {
   DPL_REQUIRE(d_xp && d_w_taps && d_w_taps_lo && d_y && tap_shift, "null pointer");
   DPL_REQUIRE(n_img > 0 && c_in > 0 && c_out > 0 && Ho > 0 && Wo > 0, "empty problem");
@@ -1655,6 +1698,10 @@ extern "C" int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, con
   p.relu = relu;
   p.error_flag = d_error_flag;
   p.Y2 = d_y_relu;
+  p.bmin = d_blob_min;
+  p.bmax = d_blob_max;
+  p.rmin = d_relu_min;
+  p.rmax = d_relu_max;
   dim3 grid((unsigned)((q_total + kBM - 1) / kBM), (unsigned)((c_out + bn - 1) / bn), 1);
   const size_t smem = (size_t)kStages3 * kStageBytes3 + 1024;
   static bool attr_done = false;

@@ -123,6 +123,19 @@ class Engine:
         st.covered.add(name)
         return (st.blob_min, st.blob_max, st.index[name])
 
+    def _uncover(self, node):
+        """A fused kernel refused the node after _rng() registered its outputs: K1 must read them."""
+        st = getattr(self, "_stats", None)
+        if st is not None:
+            st.covered.discard(node.output[0])
+            relu = self._fusable_relu(node)
+            if relu is not None:
+                st.covered.discard(relu.output[0])
+
+    def _rng_relu(self, node):
+        relu = self._fusable_relu(node)
+        return self._rng(relu.output[0]) if relu is not None else None
+
     def _native(self, x):
         return self.native_ops and torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 \
             and x.is_contiguous()
@@ -304,12 +317,17 @@ class Engine:
                     w2 = w.view(w.shape[0], w.shape[1])
                     out = self._new((x.shape[0], w.shape[0], x.shape[2], x.shape[3]), x)
                     r = self._relu_out(node, out, env)
-                    fwd = K.conv1x1_px_forward_x3 if self.conv1x1_px else K.conv1x1_forward_x3
-                    y = fwd(x, w2, self._residual(node.input[1], w2), b, out=out, out_relu=r)
+                    if self.conv1x1_px:
+                        y = K.conv1x1_px_forward_x3(x, w2, self._residual(node.input[1], w2), b, out=out, out_relu=r)
+                    else:
+                        y = K.conv1x1_forward_x3(x, w2, self._residual(node.input[1], w2), b, out=out, out_relu=r,
+                                                 rng=self._rng(node.output[0]),
+                                                 rng_relu=self._rng_relu(node) if r is not None else None)
                     self._publish_relu(node, r, env)
                     return [y]
                 except K.GemmUnsupported:
                     self._tc_off.add(node.name)
+                    self._uncover(node)
             taps_cfg = self._tc_conv_taps(node, x, w, stride, dil, lo, hi)
             if taps_cfg is not None:
                 try:
@@ -321,11 +339,14 @@ class Engine:
                     out = self._new((x.shape[0], w.shape[0], plan.ho, plan.wo), x)
                     r = self._relu_out(node, out, env)
                     y = K.conv_taps_forward_x3(x, taps, taps_lo, taps_cfg[0], taps_cfg[1], b,
-                                               scratch=self._pad_scratch, out=out, out_relu=r)
+                                               scratch=self._pad_scratch, out=out, out_relu=r,
+                                               rng=self._rng(node.output[0]),
+                                               rng_relu=self._rng_relu(node) if r is not None else None)
                     self._publish_relu(node, r, env)
                     return [y]
                 except K.GemmUnsupported:
                     self._tc_off.add(node.name)
+                    self._uncover(node)
             if (self.stem_im2col and self.tensor_cores and x.is_cuda and node.name not in self._tc_off and w.dim() == 4
                     and x.is_contiguous() and a.get("group", 1) == 1 and list(dil) == [1, 1] and sym
                     and lo[0] == lo[1] and stride[0] == stride[1] and x.shape[1] < 16
@@ -349,6 +370,7 @@ class Engine:
                     return [y]
                 except K.GemmUnsupported:
                     self._tc_off.add(node.name)
+                    self._uncover(node)
             if not sym:
                 x = F.pad(x, [p for i in reversed(range(nd)) for p in (lo[i], hi[i])])
                 lo = [0] * nd
@@ -433,9 +455,11 @@ class Engine:
                 if (self.tensor_cores and x.is_cuda and node.name not in self._tc_off and x.dim() == 2
                         and x.shape[1] % 4 == 0 and x.is_contiguous()):
                     try:
-                        return [K.linear_forward_x3(x, w, None, c, out=self._new((x.shape[0], w.shape[0]), x))]
+                        return [K.linear_forward_x3(x, w, None, c, out=self._new((x.shape[0], w.shape[0]), x),
+                                                    rng=self._rng(node.output[0]))]
                     except K.GemmUnsupported:
                         self._tc_off.add(node.name)
+                        self._uncover(node)
                 return [F.linear(x, w, c)]
             y = alpha * (x @ (w.t() if a.get("transB", 0) else w))
             return [y if c is None else y + beta * c]

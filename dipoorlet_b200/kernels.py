@@ -490,7 +490,8 @@ def tf32_residual(x):
 
 
 def gemm_tf32x3(a, a_lo, a_major, lda, a_batch_stride, b, b_major, ldb, b_batch_stride, d, ldd,
-                d_batch_stride, M, N, K, batch=1, bias=None, bias_mode=0, relu=False, d_relu=None):
+                d_batch_stride, M, N, K, batch=1, bias=None, bias_mode=0, relu=False, d_relu=None, rng=None,
+                rng_relu=None):
     dev = d.device
     flag = _gemm_err.get(dev)
     if flag is None:
@@ -499,7 +500,7 @@ def gemm_tf32x3(a, a_lo, a_major, lda, a_batch_stride, b, b_major, ldb, b_batch_
                                b.data_ptr(), int(b_major), int(ldb), int(b_batch_stride), d.data_ptr(),
                                int(ldd), int(d_batch_stride), int(M), int(N), int(K), int(batch),
                                _lib._ptr(bias), int(bias_mode), int(bool(relu)), _lib._ptr(d_relu),
-                               flag.data_ptr(), _stream())
+                               *_rng(rng), *_rng(rng_relu), flag.data_ptr(), _stream())
     if st == 10003:
         raise GemmUnsupported(lib().dpl_last_error().decode("utf-8", "replace"))
     check(st, "dpl_gemm_tf32x3")
@@ -507,7 +508,7 @@ def gemm_tf32x3(a, a_lo, a_major, lda, a_batch_stride, b, b_major, ldb, b_batch_
     return d
 
 
-def conv1x1_forward_x3(x, w, w_lo, bias=None, relu=False, out=None, out_relu=None):
+def conv1x1_forward_x3(x, w, w_lo, bias=None, relu=False, out=None, out_relu=None, rng=None, rng_relu=None):
     """fp32-accurate O[img][co][hw] = W[co][ci] x X[img][ci][hw] (+ bias[co]) on tensor cores;
     `out_relu` (same shape) also receives max(O, 0)."""
     n, ci, hh, ww = x.shape
@@ -516,7 +517,8 @@ def conv1x1_forward_x3(x, w, w_lo, bias=None, relu=False, out=None, out_relu=Non
     o = torch.empty((n, co, hh, ww), dtype=torch.float32, device=x.device) if out is None else out
     _need(out_relu, torch.float32, "out_relu")
     return gemm_tf32x3(w, w_lo, 0, ci, 0, x, 1, hw, ci * hw, o, hw, co * hw, co, hw, ci, batch=n,
-                       bias=bias, bias_mode=1 if bias is not None else 0, relu=relu, d_relu=out_relu)
+                       bias=bias, bias_mode=1 if bias is not None else 0, relu=relu, d_relu=out_relu, rng=rng,
+                       rng_relu=rng_relu)
 
 
 def conv1x1_px_forward_x3(x, w, w_lo, bias=None, out=None, out_relu=None):
@@ -542,14 +544,14 @@ def conv1x1_px_forward_x3(x, w, w_lo, bias=None, out=None, out_relu=None):
     return o
 
 
-def linear_forward_x3(x, w, w_lo=None, bias=None, out=None):
+def linear_forward_x3(x, w, w_lo=None, bias=None, out=None, rng=None):
     """fp32-accurate Y = X W^T (+ bias): A = X (its residual is computed here, X is small),
     B = W is split inside the kernel, so `w_lo` is not needed."""
     nrow, k = x.shape
     out_f = w.shape[0]
     y = torch.empty((nrow, out_f), dtype=torch.float32, device=x.device) if out is None else out
     return gemm_tf32x3(x, tf32_residual(x), 0, k, 0, w, 0, k, 0, y, out_f, 0, nrow, out_f, k, batch=1,
-                       bias=bias, bias_mode=2 if bias is not None else 0)
+                       bias=bias, bias_mode=2 if bias is not None else 0, rng=rng)
 
 
 def conv_taps_prepare(w):
@@ -592,7 +594,7 @@ def conv3x3_plane_pitch(h, w):
 
 
 def conv_taps_forward_x3(x, taps, taps_lo, ksize, stride, bias=None, relu=False, out=None, scratch=None,
-                         out_relu=None):
+                         out_relu=None, rng=None, rng_relu=None):
     """fp32-accurate 3x3 (stride 1 or 2, pad 1) or strided 1x1 convolution on the tensor cores:
     channel-last staging copy of x (dpl_pad_plane_f32), then the shifted-window GEMM."""
     n, ci, hh, ww = x.shape
@@ -612,7 +614,7 @@ def conv_taps_forward_x3(x, taps, taps_lo, ksize, stride, bias=None, relu=False,
     st = lib().dpl_conv_taps_tf32x3(scratch.data_ptr(), plan.total_rows, taps.data_ptr(), taps_lo.data_ptr(),
                                     y.data_ptr(), n, ci, co, plan.ho, plan.wo, plan.hp, plan.wp, plan.origin,
                                     len(plan.shifts), plan.c_shifts, _lib._ptr(bias), int(bool(relu)),
-                                    _lib._ptr(out_relu), flag.data_ptr(), _stream())
+                                    _lib._ptr(out_relu), *_rng(rng), *_rng(rng_relu), flag.data_ptr(), _stream())
     if st == 10003:
         raise GemmUnsupported(lib().dpl_last_error().decode("utf-8", "replace"))
     check(st, "dpl_conv_taps_tf32x3")
@@ -654,7 +656,7 @@ def conv_im2col_forward_x3(x, prepared, kernel, stride, pad, bias=None, out=None
     shifts = (ctypes.c_int * 1)(0)
     st = lib().dpl_conv_taps_tf32x3(scratch.data_ptr(), rows, w2.data_ptr(), w2_lo.data_ptr(), y.data_ptr(), n, k_pad,
                                     co, ho, wo, ho, wo, 0, 1, shifts, _lib._ptr(bias), 0, _lib._ptr(out_relu),
-                                    flag.data_ptr(), _stream())
+                                    0, 0, 0, 0, flag.data_ptr(), _stream())
     if st == 10003:
         raise GemmUnsupported(lib().dpl_last_error().decode("utf-8", "replace"))
     check(st, "dpl_conv_taps_tf32x3")

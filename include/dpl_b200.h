@@ -222,13 +222,16 @@ int dpl_gemm_tf32(const float* d_a, int a_major, long long lda, long long a_batc
  * fp32 ORT path, dipoorlet/forward_net.py:200-216). d_a_lo = dpl_tf32_residual_f32(d_a) is
  * computed once per weight; the residual of B is formed in shared memory inside the kernel.
  * d_d_relu (optional): a second output max(D, 0) with D's layout — the Relu node behind a Conv is
- * a calibration blob of its own, so the epilogue writes both instead of a second pass. */
+ * a calibration blob of its own, so the epilogue writes both instead of a second pass.
+ * d_blob_min / d_blob_max / d_relu_min / d_relu_max (optional, one float each): fused range statistics of D
+ * and of the Relu output, as in dpl_clip_f32 (same arguments on dpl_conv_taps_tf32x3). */
 int dpl_tf32_residual_f32(const float* d_x, float* d_lo, uint64_t n, void* stream);
 int dpl_gemm_tf32x3(const float* d_a, const float* d_a_lo, int a_major, long long lda,
                     long long a_batch_stride, const float* d_b, int b_major, long long ldb,
                     long long b_batch_stride, float* d_d, long long ldd, long long d_batch_stride,
                     int M, int N, int K, int batch, const float* d_bias, int bias_mode, int relu,
-                    float* d_d_relu, int* d_error_flag, void* stream);
+                    float* d_d_relu, float* d_blob_min, float* d_blob_max, float* d_relu_min,
+                    float* d_relu_max, int* d_error_flag, void* stream);
 
 /* k x k / strided convolutions of the calibration forward (the Conv nodes that ORT executes in
  * dipoorlet/forward_net.py:200-216), fp32-accurate (3xTF32) on the tcgen05 tensor cores as a
@@ -250,7 +253,8 @@ int dpl_pad_plane_f32(const float* d_x, float* d_xp, int n_img, int channels, in
 int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, const float* d_w_taps,
                          const float* d_w_taps_lo, float* d_y, int n_img, int c_in, int c_out, int Ho,
                          int Wo, int Hp, int Wp, int origin, int n_taps, const int* tap_shift,
-                         const float* d_bias, int relu, float* d_y_relu, int* d_error_flag, void* stream);
+                         const float* d_bias, int relu, float* d_y_relu, float* d_blob_min, float* d_blob_max,
+                         float* d_relu_min, float* d_relu_max, int* d_error_flag, void* stream);
 
 /* im2col staging for a convolution with very few input channels (ResNet's 7x7 / stride 2 stem, 3
  * channels): d_xp[(img * Ho + ho) * Wo + wo][(c * kh + a) * kw + b] = X[img][c][ho * stride - pad + a]
