@@ -192,9 +192,22 @@ def run_ours(args):
     from dipoorlet_b200.graph import ONNXGraph
     from dipoorlet_b200.tensor_cali import tensor_calibration
 
-    rank, local_rank, world = dist_helper.init_from_env()
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
+    # stdout carries exactly ONE JSON line: NCCL announces its version on stdout at the first collective
+    # (NCCL_DEBUG=VERSION in this image), so file descriptor 1 points at stderr until that has happened
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rank, local_rank, world = dist_helper.init_from_env()
+        dev = torch.device("cuda", local_rank)
+        torch.cuda.set_device(dev)
+        if world > 1:
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     n_img = args.images
     model = W.build_resnet50(seed=0)
     graph = ONNXGraph(model, "/tmp/dpl_bench", "trt")
@@ -303,9 +316,9 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "images_per_gpu": n_img, "forward_batch": args.batch,
                    "l2": "inputs larger than L2: every timed kernel streams a %.1f GB batch of blobs "
                          "(126 MB L2)" % (4 * elems_per_img * args.batch / 1e9),
-                   "forward": ("libdpl_b200: 1x1 / 3x3 / strided conv + Gemm on tcgen05 3xTF32 tiles (fp32-accurate), Relu / Add / "
-                               "MaxPool / GlobalAveragePool streaming kernels with fused range statistics; 7x7 stem conv: "
-                               "torch/cuDNN fp32 stand-in (TF32 off)") if os.environ.get("DPL_ENGINE_TCGEN05", "1") != "0"
+                   "forward": ("libdpl_b200 only: 1x1 / 3x3 / strided conv + Gemm on tcgen05 3xTF32 tiles (fp32-accurate), 7x7 stem "
+                               "conv on a direct fp32 kernel, Relu / Add / MaxPool / GlobalAveragePool streaming kernels; range "
+                               "statistics fused into all of their epilogues") if os.environ.get("DPL_ENGINE_TCGEN05", "1") != "0"
                    else "torch/cuDNN fp32 (TF32 off) stand-in producer",
                    "statistics": "libdpl_b200.so (K1 segstats on the blobs the forward's kernels did not cover, K2 histogram "
                                  "variant 7, K3 percentile)",

@@ -82,6 +82,9 @@ SIGNATURES = {
                                       _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_int,
                                       _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "dpl_mix_drop_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_u64, _c_flt, _c_u64, _c_vp]),
+    "dpl_conv_direct_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                     _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
+                                     _c_vp]),
     "dpl_im2col_f32": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                 _c_int, _c_int, _c_int, _c_vp]),
     "dpl_conv1x1_px_tf32x3": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp,

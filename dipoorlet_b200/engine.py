@@ -7,12 +7,13 @@ promoted to a graph output and copied back to the host (dipoorlet/forward_net.py
 and the per-node sessions of ActivationCache.forward_subnet (forward_net.py:81-128).
 
 1x1 / 3x3 / strided convolutions and Gemm layers run on libdpl_b200's tcgen05 tiles in 3xTF32 mode
-(fp32-accurate products on the TF32 tensor cores); Relu / Clip / Add (+ the Relu behind it) /
-MaxPool / GlobalAveragePool are libdpl_b200 streaming kernels (dpl_eltwise.cu). STAND-IN NOTICE
-(SURVEY.md §7 step 5, §8 f2): what the tiles do not cover yet (the 7x7 stem convolution,
-depthwise / grouped convolutions, rarely used operators) is still issued through torch's CUDA
-ops (cuDNN, true fp32: TF32 disabled), i.e. a library call playing the role onnxruntime's CUDA
-EP plays in the reference. QuantizeLinear + DequantizeLinear pairs are ONE fused K5 launch.
+(fp32-accurate products on the TF32 tensor cores); the few-channel stem convolution on a direct fp32
+kernel (dpl_conv_direct.cu); Relu / Clip / Add (+ the Relu behind it) / MaxPool / GlobalAveragePool
+are libdpl_b200 streaming kernels (dpl_eltwise.cu) — a ResNet-50 forward issues no library kernel.
+STAND-IN NOTICE: what these do not cover yet (depthwise / grouped
+convolutions of MobileNetV2, rarely used operators) is still issued through torch's CUDA ops (cuDNN,
+true fp32: TF32 disabled), i.e. a library call playing the role onnxruntime's CUDA EP plays in the
+reference. QuantizeLinear + DequantizeLinear pairs are ONE fused K5 launch.
 
 Blob memory: when `engine.arena` is set (forward_net.CalibrationSession does) every node output is
 bump-allocated from that one slab instead of torch's caching allocator.
@@ -79,6 +80,8 @@ class Engine:
         # and tested, measured slower than cuDNN's fp32 kernel (1.05 vs 0.81 ms per 64 images: the staging
         # copy is 475 MB), so opt-in until the gather moves into the kernel
         self.stem_im2col = os.environ.get("DPL_ENGINE_STEM_IM2COL", "0") == "1"
+        # few-channel stem convolution on libdpl_b200's direct fp32 kernel (Relu blob from its epilogue)
+        self.stem_direct = os.environ.get("DPL_ENGINE_STEM_DIRECT", "1") != "0"
 
     # ------------------------------------------------------------------ blob memory
     def _new(self, shape, like):
@@ -102,9 +105,10 @@ class Engine:
         o.copy_(v)
         return o
 
-    def _relu_out(self, node, like, env):
-        """Buffer for the fused Relu blob behind `node`, or None when there is nothing to fuse."""
-        if not self.native_ops or not self.fuse_conv_relu:
+    def _relu_out(self, node, like, env, always=False):
+        """Buffer for the fused Relu blob behind `node`, or None when there is nothing to fuse.
+        always=True: the producer's epilogue is not the bottleneck (direct stem convolution)."""
+        if not self.native_ops or not (self.fuse_conv_relu or always):
             return None
         relu = self._fusable_relu(node)
         if relu is None or relu.output[0] in env:
@@ -342,6 +346,23 @@ class Engine:
                                                scratch=self._pad_scratch, out=out, out_relu=r,
                                                rng=self._rng(node.output[0]),
                                                rng_relu=self._rng_relu(node) if r is not None else None)
+                    self._publish_relu(node, r, env)
+                    return [y]
+                except K.GemmUnsupported:
+                    self._tc_off.add(node.name)
+                    self._uncover(node)
+            if (self.stem_direct and x.is_cuda and node.name not in self._tc_off and w.dim() == 4 and x.dim() == 4
+                    and x.is_contiguous() and w.is_contiguous() and a.get("group", 1) == 1 and list(dil) == [1, 1]
+                    and sym and lo[0] == lo[1] and stride[0] == stride[1] and w.shape[2] == w.shape[3]
+                    and x.shape[1] <= 4 and (int(w.shape[2]), int(stride[0])) in ((7, 2), (5, 1), (5, 2), (3, 1), (3, 2))):
+                try:   # few input channels (the stem): exact-fp32 direct convolution on the FMA pipe
+                    ho = (x.shape[2] + 2 * lo[0] - w.shape[2]) // stride[0] + 1
+                    wo = (x.shape[3] + 2 * lo[1] - w.shape[3]) // stride[1] + 1
+                    out = self._new((x.shape[0], w.shape[0], ho, wo), x)
+                    r = self._relu_out(node, out, env, always=True)
+                    y = K.conv_direct_forward(x, w, b, int(stride[0]), int(lo[0]), out=out, out_relu=r,
+                                              rng=self._rng(node.output[0]),
+                                              rng_relu=self._rng_relu(node) if r is not None else None)
                     self._publish_relu(node, r, env)
                     return [y]
                 except K.GemmUnsupported:

@@ -622,6 +622,26 @@ def conv_taps_forward_x3(x, taps, taps_lo, ksize, stride, bias=None, relu=False,
     return y
 
 
+def conv_direct_forward(x, w, bias, stride, pad, out=None, out_relu=None, rng=None, rng_relu=None):
+    """Exact-fp32 direct convolution for few input channels (the stem), see dpl_conv_direct_f32."""
+    _need(x, torch.float32, "x")
+    _need(w, torch.float32, "w")
+    n, c, hh, ww = x.shape
+    co, _, kh, kw = w.shape
+    ho, wo = (hh + 2 * pad - kh) // stride + 1, (ww + 2 * pad - kw) // stride + 1
+    y = torch.empty((n, co, ho, wo), dtype=torch.float32, device=x.device) if out is None else out
+    _need(y, torch.float32, "out")
+    _need(out_relu, torch.float32, "out_relu")
+    st = lib().dpl_conv_direct_f32(x.data_ptr(), w.data_ptr(), _lib._ptr(bias), y.data_ptr(), n, c, hh, ww, co, kh, kw,
+                                   int(stride), int(pad), ho, wo, _lib._ptr(out_relu), *_rng(rng), *_rng(rng_relu),
+                                   _stream())
+    if st == 10003:
+        raise GemmUnsupported(lib().dpl_last_error().decode("utf-8", "replace"))
+    check(st, "dpl_conv_direct_f32")
+    _count()
+    return y
+
+
 def conv_im2col_prepare(w):
     """[co][C][kh][kw] filter -> ([1][co][k_pad] row-major copy zero-padded to a multiple of 4, its
     TF32 residual, k_pad) for conv_im2col_forward_x3 (once per weight)."""

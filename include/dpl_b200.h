@@ -256,6 +256,18 @@ int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, const float* d
                          const float* d_bias, int relu, float* d_y_relu, float* d_blob_min, float* d_blob_max,
                          float* d_relu_min, float* d_relu_max, int* d_error_flag, void* stream);
 
+/* Direct fp32 convolution for layers with very few input channels (ResNet's 7x7 / stride 2 stem,
+ * MobileNetV2's 3x3 / stride 2 stem on the 3 image channels; the Conv node ORT executes in
+ * dipoorlet/forward_net.py:200-216): exact fp32 FMA accumulation like the reference's CPU path,
+ * input patch + transposed filter in shared memory, 4 pixels x 16 channels per thread.
+ *   Y[img][co][ho][wo] = bias[co] + sum W[co][c][a][b] * X[img][c][ho * stride - pad + a][wo * stride - pad + b]
+ * (kh, kw, stride) in {(7,7,2), (5,5,1|2), (3,3,1|2)}, symmetric padding; DPL_E_UNSUPPORTED otherwise or when the
+ * patch + filter exceed 100 KB of shared memory. d_y_relu / d_blob_* / d_relu_*: as in dpl_gemm_tf32x3. */
+int dpl_conv_direct_f32(const float* d_x, const float* d_w, const float* d_bias, float* d_y, int n_img,
+                        int channels, int H, int W, int c_out, int kh, int kw, int stride, int pad, int Ho,
+                        int Wo, float* d_y_relu, float* d_blob_min, float* d_blob_max, float* d_relu_min,
+                        float* d_relu_max, void* stream);
+
 /* im2col staging for a convolution with very few input channels (ResNet's 7x7 / stride 2 stem, 3
  * channels): d_xp[(img * Ho + ho) * Wo + wo][(c * kh + a) * kw + b] = X[img][c][ho * stride - pad + a]
  * [wo * stride - pad + b] (0 outside, 0 for columns >= C kh kw); k_pad a multiple of 4, <= 256. The

@@ -165,6 +165,40 @@ def test_conv_im2col_stem_3xtf32_is_fp32_accurate(dpl_built, cfg):
     assert err <= max(3 * err32, 2e-6 * scale), (err, err32, scale)
 
 
+@pytest.mark.parametrize("cfg", [(4, 3, 64, 64, 7, 2, 3), (2, 3, 16, 33, 7, 2, 3), (3, 1, 8, 20, 5, 1, 2),
+                                 (2, 4, 40, 18, 3, 2, 1), (2, 3, 32, 37, 3, 2, 1), (1, 3, 70, 21, 3, 1, 1),
+                                 (2, 2, 24, 30, 5, 2, 2)])
+def test_conv_direct_stem_is_exact_fp32(dpl_built, cfg):
+    """Direct few-channel convolution (the stem): fp32 FMA accumulation, so it must sit at the accuracy of
+    cuDNN's fp32 kernel against float64; ragged tiles, channel tails (c_out = 70 spans two channel tiles,
+    8 / 24 / 40 leave part of one empty), the fused Relu output and the fused range statistics."""
+    import torch
+    import torch.nn.functional as F
+    from dipoorlet_b200 import kernels as K
+    n, ci, co, hw, k, stride, pad = cfg
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = torch.randn((n, ci, hw, hw + 3), device="cuda", generator=g)
+    w = torch.randn((co, ci, k, k), device="cuda", generator=g) * 0.1
+    b = torch.randn(co, device="cuda", generator=g)
+    lo = torch.full((2,), float("inf"), device="cuda")
+    hi = torch.full((2,), float("-inf"), device="cuda")
+    want = F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=pad)
+    out = torch.full(want.shape, float("nan"), device="cuda")
+    out_relu = torch.full(want.shape, float("nan"), device="cuda")
+    o = K.conv_direct_forward(x, w, b, stride, pad, out=out, out_relu=out_relu, rng=(lo, hi, 0), rng_relu=(lo, hi, 1))
+    assert not torch.isnan(o).any()
+    assert torch.equal(out_relu, torch.relu(o))
+    assert lo.tolist() == [o.min().item(), out_relu.min().item()]
+    assert hi.tolist() == [o.max().item(), out_relu.max().item()]
+    torch.backends.cudnn.allow_tf32 = False
+    ref32 = F.conv2d(x, w, b, stride=stride, padding=pad)
+    err = (o.double() - want).abs().max().item()
+    err32 = (ref32.double() - want).abs().max().item()
+    assert err <= max(2 * err32, 1e-6 * want.abs().max().item()), (err, err32)
+    o2 = K.conv_direct_forward(x, w, None, stride, pad)
+    assert torch.allclose(o2, o - b.view(1, -1, 1, 1), rtol=0, atol=1e-5)
+
+
 def test_linear_forward_3xtf32(dpl_built):
     import torch
     from dipoorlet_b200 import kernels as K
