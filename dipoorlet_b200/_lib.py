@@ -85,6 +85,8 @@ SIGNATURES = {
     "dpl_conv_direct_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                      _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
                                      _c_vp]),
+    "dpl_dwconv2d_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                  _c_int, _c_int, _c_vp, _c_vp, _c_vp]),
     "dpl_im2col_f32": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                 _c_int, _c_int, _c_int, _c_vp]),
     "dpl_conv1x1_px_tf32x3": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp,

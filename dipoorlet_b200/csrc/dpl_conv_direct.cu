@@ -190,6 +190,62 @@ int launch_direct(const DcParams& p, cudaStream_t st) {
   return cuda_status(cudaGetLastError(), "conv_direct_kernel");
 }
 
+
+// ---- depthwise convolution (MobileNetV2's 3x3 group = C layers) -------------------------------
+// One multiply-add per filter tap and output: purely HBM bound, nothing for the tensor cores. One
+// thread per output, a CTA inside one (image, channel) plane (filter taps and bias are CTA-uniform:
+// registers), windows inside the image skip the bounds checks; fp32 FMA chain in tap order.
+template <int K>
+__global__ void __launch_bounds__(256)
+dwconv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+              float* __restrict__ y, uint32_t tiles_per_plane, int C, int H, int W, int stride, int pad, int Ho,
+              int Wo, float* __restrict__ bmin, float* __restrict__ bmax) {
+  const uint32_t plane = blockIdx.x / tiles_per_plane;
+  const uint32_t tile = blockIdx.x - plane * tiles_per_plane;
+  const int c = (int)(plane % (uint32_t)C);
+  float wt[K * K];
+#pragma unroll
+  for (int i = 0; i < K * K; ++i) wt[i] = __ldg(w + (long long)c * K * K + i);
+  const float b0 = bias ? __ldg(bias + c) : 0.f;
+  const uint32_t idx = tile * 256u + threadIdx.x;
+  float rlo = INFINITY, rhi = -INFINITY;
+  if (idx < (uint32_t)(Ho * Wo)) {
+    const int ho = (int)(idx / (uint32_t)Wo), wo = (int)(idx - (uint32_t)ho * (uint32_t)Wo);
+    const float* xp = x + (uint64_t)plane * (uint32_t)(H * W);
+    const int h0 = ho * stride - pad, w0 = wo * stride - pad;
+    float acc = 0.f;
+    if (h0 >= 0 && w0 >= 0 && h0 + K <= H && w0 + K <= W) {
+      const float* q = xp + h0 * W + w0;
+#pragma unroll
+      for (int a = 0; a < K; ++a)
+#pragma unroll
+        for (int b = 0; b < K; ++b) acc = fmaf(__ldg(q + a * W + b), wt[a * K + b], acc);
+    } else {
+#pragma unroll
+      for (int a = 0; a < K; ++a) {
+        const int h = h0 + a;
+#pragma unroll
+        for (int b = 0; b < K; ++b) {
+          const int ww = w0 + b;
+          const float v = (h >= 0 && h < H && ww >= 0 && ww < W) ? __ldg(xp + h * W + ww) : 0.f;
+          acc = fmaf(v, wt[a * K + b], acc);
+        }
+      }
+    }
+    acc += b0;
+    y[(uint64_t)plane * (uint32_t)(Ho * Wo) + idx] = acc;
+    rlo = rhi = acc;
+  }
+  if (bmin || bmax) {   // every lane takes part
+    rlo = warp_min(rlo);
+    rhi = warp_max(rhi);
+    if ((threadIdx.x & 31) == 0 && rlo <= rhi) {
+      if (bmin) atomic_min_f32(bmin, rlo + 0.f);
+      if (bmax) atomic_max_f32(bmax, rhi + 0.f);
+    }
+  }
+}
+
 }  // namespace
 }  // namespace dpl
 
@@ -232,4 +288,31 @@ extern "C" int dpl_conv_direct_f32(const float* d_x, const float* d_w, const flo
   if (kh == 5 && kw == 5 && stride == 1) return launch_direct<5, 5, 1>(p, st);
   set_error("dpl_conv_direct_f32: kernel %dx%d stride %d is not instantiated", kh, kw, stride);
   return DPL_E_UNSUPPORTED;
+}
+
+// Depthwise convolution, group = channels = c_out, depth multiplier 1 (MobileNetV2's 3x3 layers):
+//   Y[img][c][ho][wo] = bias[c] + sum_{a,b} W[c][0][a][b] * X[img][c][ho * stride - pad + a][wo * stride - pad + b]
+// k in {3, 5}, symmetric padding; d_blob_min / d_blob_max: fused range statistics as in dpl_clip_f32.
+extern "C" int dpl_dwconv2d_f32(const float* d_x, const float* d_w, const float* d_bias, float* d_y, int n_img,
+                                int channels, int H, int W, int k, int stride, int pad, int Ho, int Wo,
+                                float* d_blob_min, float* d_blob_max, void* stream) {
+  DPL_REQUIRE(d_x && d_w && d_y, "null pointer");
+  DPL_REQUIRE(n_img > 0 && channels > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && stride > 0 && pad >= 0, "bad geometry");
+  DPL_REQUIRE((long long)H * W < (1ll << 31) && (long long)Ho * Wo < (1ll << 31), "plane too large");
+  const uint64_t planes = (uint64_t)n_img * channels;
+  const uint64_t tiles_per_plane = ((uint64_t)Ho * Wo + 255) / 256;
+  DPL_REQUIRE(planes * tiles_per_plane < (1ull << 31), "too many tiles");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (k == 3)
+    dwconv_kernel<3><<<(unsigned)(planes * tiles_per_plane), 256, 0, st>>>(
+        d_x, d_w, d_bias, d_y, (uint32_t)tiles_per_plane, channels, H, W, stride, pad, Ho, Wo, d_blob_min, d_blob_max);
+  else if (k == 5)
+    dwconv_kernel<5><<<(unsigned)(planes * tiles_per_plane), 256, 0, st>>>(
+        d_x, d_w, d_bias, d_y, (uint32_t)tiles_per_plane, channels, H, W, stride, pad, Ho, Wo, d_blob_min, d_blob_max);
+  else {
+    set_error("dpl_dwconv2d_f32: kernel size %d is not instantiated", k);
+    return DPL_E_UNSUPPORTED;
+  }
+  DPL_LAUNCH_CHECK("dwconv_kernel");
+  return 0;
 }

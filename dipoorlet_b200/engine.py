@@ -352,6 +352,19 @@ class Engine:
                     self._tc_off.add(node.name)
                     self._uncover(node)
             if (self.stem_direct and x.is_cuda and node.name not in self._tc_off and w.dim() == 4 and x.dim() == 4
+                    and x.is_contiguous() and w.is_contiguous() and a.get("group", 1) == x.shape[1] == w.shape[0]
+                    and w.shape[1] == 1 and x.shape[1] > 1 and list(dil) == [1, 1] and sym and lo[0] == lo[1]
+                    and stride[0] == stride[1] and w.shape[2] == w.shape[3] and int(w.shape[2]) in (3, 5)):
+                try:   # depthwise convolution: one streaming pass
+                    ho = (x.shape[2] + 2 * lo[0] - w.shape[2]) // stride[0] + 1
+                    wo = (x.shape[3] + 2 * lo[1] - w.shape[3]) // stride[1] + 1
+                    out = self._new((x.shape[0], w.shape[0], ho, wo), x)
+                    return [K.dwconv2d_forward(x, w, b, int(stride[0]), int(lo[0]), out=out,
+                                               rng=self._rng(node.output[0]))]
+                except K.GemmUnsupported:
+                    self._tc_off.add(node.name)
+                    self._uncover(node)
+            if (self.stem_direct and x.is_cuda and node.name not in self._tc_off and w.dim() == 4 and x.dim() == 4
                     and x.is_contiguous() and w.is_contiguous() and a.get("group", 1) == 1 and list(dil) == [1, 1]
                     and sym and lo[0] == lo[1] and stride[0] == stride[1] and w.shape[2] == w.shape[3]
                     and x.shape[1] <= 4 and (int(w.shape[2]), int(stride[0])) in ((7, 2), (5, 1), (5, 2), (3, 1), (3, 2))):

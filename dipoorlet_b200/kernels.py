@@ -642,6 +642,24 @@ def conv_direct_forward(x, w, bias, stride, pad, out=None, out_relu=None, rng=No
     return y
 
 
+def dwconv2d_forward(x, w, bias, stride, pad, out=None, rng=None):
+    """Depthwise convolution (group = channels), see dpl_dwconv2d_f32."""
+    _need(x, torch.float32, "x")
+    _need(w, torch.float32, "w")
+    n, c, hh, ww = x.shape
+    k = int(w.shape[2])
+    ho, wo = (hh + 2 * pad - k) // stride + 1, (ww + 2 * pad - k) // stride + 1
+    y = torch.empty((n, c, ho, wo), dtype=torch.float32, device=x.device) if out is None else out
+    _need(y, torch.float32, "out")
+    st = lib().dpl_dwconv2d_f32(x.data_ptr(), w.data_ptr(), _lib._ptr(bias), y.data_ptr(), n, c, hh, ww, k,
+                                int(stride), int(pad), ho, wo, *_rng(rng), _stream())
+    if st == 10003:
+        raise GemmUnsupported(lib().dpl_last_error().decode("utf-8", "replace"))
+    check(st, "dpl_dwconv2d_f32")
+    _count()
+    return y
+
+
 def conv_im2col_prepare(w):
     """[co][C][kh][kw] filter -> ([1][co][k_pad] row-major copy zero-padded to a multiple of 4, its
     TF32 residual, k_pad) for conv_im2col_forward_x3 (once per weight)."""

@@ -268,6 +268,13 @@ int dpl_conv_direct_f32(const float* d_x, const float* d_w, const float* d_bias,
                         int Wo, float* d_y_relu, float* d_blob_min, float* d_blob_max, float* d_relu_min,
                         float* d_relu_max, void* stream);
 
+/* Depthwise convolution (group = channels = c_out, depth multiplier 1; MobileNetV2's 3x3 layers, the
+ * same ORT Conv node): one FMA per tap and output, HBM bound, k in {3, 5}, symmetric padding.
+ * d_w: [channels][1][k][k]. d_blob_min / d_blob_max: fused range statistics as in dpl_clip_f32. */
+int dpl_dwconv2d_f32(const float* d_x, const float* d_w, const float* d_bias, float* d_y, int n_img,
+                     int channels, int H, int W, int k, int stride, int pad, int Ho, int Wo,
+                     float* d_blob_min, float* d_blob_max, void* stream);
+
 /* im2col staging for a convolution with very few input channels (ResNet's 7x7 / stride 2 stem, 3
  * channels): d_xp[(img * Ho + ho) * Wo + wo][(c * kh + a) * kw + b] = X[img][c][ho * stride - pad + a]
  * [wo * stride - pad + b] (0 outside, 0 for columns >= C kh kw); k_pad a multiple of 4, <= 256. The

@@ -199,6 +199,26 @@ def test_conv_direct_stem_is_exact_fp32(dpl_built, cfg):
     assert torch.allclose(o2, o - b.view(1, -1, 1, 1), rtol=0, atol=1e-5)
 
 
+@pytest.mark.parametrize("cfg", [(3, 32, 56, 3, 1), (2, 96, 57, 3, 2), (2, 7, 9, 5, 1), (1, 16, 14, 5, 2)])
+def test_depthwise_conv_is_exact_fp32(dpl_built, cfg):
+    import torch
+    import torch.nn.functional as F
+    from dipoorlet_b200 import kernels as K
+    n, c, hw, k, stride = cfg
+    pad = k // 2
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn((n, c, hw, hw + 1), device="cuda", generator=g)
+    w = torch.randn((c, 1, k, k), device="cuda", generator=g) * 0.3
+    b = torch.randn(c, device="cuda", generator=g)
+    lo = torch.full((1,), float("inf"), device="cuda")
+    hi = torch.full((1,), float("-inf"), device="cuda")
+    o = K.dwconv2d_forward(x, w, b, stride, pad, rng=(lo, hi, 0))
+    want = F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=pad, groups=c)
+    assert o.shape == want.shape
+    assert (o.double() - want).abs().max().item() <= 2e-6 * want.abs().max().item()
+    assert lo.item() == o.min().item() and hi.item() == o.max().item()
+
+
 def test_linear_forward_3xtf32(dpl_built):
     import torch
     from dipoorlet_b200 import kernels as K
