@@ -72,3 +72,26 @@ def test_oracle_bias_correction_equals_reference(mname, tmp_path):
     for k in gold.files:
         assert np.array_equal(got[k].astype(np.float32), gold[k].astype(np.float32)), \
             (k, np.abs(got[k] - gold[k]).max())
+
+
+@pytest.mark.parametrize("mname", ["tiny_r50", "tiny_mbv2"])
+def test_weight_equalization_equals_reference(mname, tmp_path):
+    """`--we` (weight_equalization.py:36-94): the product's array-expression form must rewrite exactly
+    the initializers the reference rewrote, bit for bit (tests/golden/*/wt_we.npz, produced by running
+    the reference's own weight_calibration(we=True), oracle/gen_golden_we.py)."""
+    from dipoorlet_b200.weight_transform.weight_equalization import node_has_equalized, weight_equalization
+    d, model, images, clip, graph, args = _setup(mname, tmp_path)
+    before = {k: np.asarray(v).copy() for k, v in model.graph.initializers.items()}
+    g2 = weight_equalization(graph, args)
+    assert os.path.exists(os.path.join(str(tmp_path), "weight_equal_model.onnx"))
+    after = {k: np.asarray(g2.get_initializer(k)) for k in before}
+    changed = {k: v for k, v in after.items() if not np.array_equal(before[k], v)}
+    gold = np.load(os.path.join(d, "wt_we.npz"))
+    assert sorted(changed) == sorted(gold.files)
+    for k in gold.files:
+        assert changed[k].dtype == gold[k].dtype and np.array_equal(changed[k], gold[k]), \
+            (k, np.abs(changed[k] - gold[k]).max())
+    # the input graph is untouched (the reference equalises a copy, :37-38)
+    for k, v in before.items():
+        assert np.array_equal(np.asarray(graph.get_initializer(k)), v)
+    assert any(node_has_equalized(graph, n) for n in graph.graph.node if n.op_type == "Conv")

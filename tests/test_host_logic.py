@@ -93,3 +93,36 @@ def test_shard_range_follows_reference_floor_rule():
         a.rank = r
         got.append(shard_range(a))
     assert got == [(0, 2), (2, 4), (4, 6), (6, 8)]  # the tail (8, 9) is dropped, forward_net.py:207-209
+
+
+@pytest.mark.parametrize("mname", ["tiny_r50", "tiny_mbv2"])
+def test_weight_calibration_we_recalibrates_like_the_reference(mname, monkeypatch, tmp_path):
+    """weight_calibration(--we) end to end on the CPU stand-ins: equalise, save / reload the model,
+    re-calibrate (weight_trans_base.py:31-36). The activation clip values of the re-calibration must be
+    the reference's own (tests/golden/*/wt_we_clip.json, oracle/gen_golden_we.py) within fp32 rounding
+    of the batched forward, in the reference's key order."""
+    from dipoorlet_b200 import forward_net as fwd
+    from dipoorlet_b200 import onnx_lite as ol
+    from dipoorlet_b200 import workloads as W
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.tensor_cali import tensor_calibration
+    from dipoorlet_b200.weight_transform import weight_calibration
+    monkeypatch.setattr(fwd, "K", fake_kernels)
+    fwd._SESSIONS.clear()
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", mname)
+    model = ol.load(os.path.join(gold_dir, "model.onnx"))
+    images = np.load(os.path.join(gold_dir, "images.npy"))
+    W.write_input_dir(images, str(tmp_path / "data"), "input")
+    graph = ONNXGraph(model, str(tmp_path), "trt")
+    args = make_args(input_dir=str(tmp_path / "data"), data_num=images.shape[0], deploy="trt", act_quant="minmax",
+                     output_dir=str(tmp_path), calib_bs=3, _test_device="cpu", we=True)
+    act, weight = tensor_calibration(graph, args)
+    g2, g_ori, act2, weight2 = weight_calibration(graph, act, weight, args)
+    assert g_ori is graph and os.path.exists(os.path.join(str(tmp_path), "weight_equal_model.onnx"))
+    gold = json.load(open(os.path.join(gold_dir, "wt_we_clip.json")))
+    assert list(act2) == list(gold)
+    for k, v in gold.items():
+        assert np.allclose([act2[k][0], act2[k][1]], v, rtol=1e-5, atol=1e-6), (k, act2[k], v)
+    changed = [k for k in act if not np.allclose(act[k], act2[k], rtol=1e-4, atol=1e-6)]
+    assert changed      # equalisation moved the ranges of the blobs between the paired layers
