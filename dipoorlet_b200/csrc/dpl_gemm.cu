@@ -575,6 +575,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // Leading term in ONE accumulator: the tensor core accumulates with truncation, which costs
 // ~3e-9 relative per K step (measured, tools/x3_accuracy.py) - below fp32 rounding for K <= 512.
 constexpr int kGemmPThreads = 384;
+constexpr int kStgPitch = 36;                                  // floats per staged row: 16-byte aligned, conflict free
+constexpr int kStgBytes = 4 * 32 * kStgPitch * 4;              // one 32 x 32 staging tile per epilogue warp
 
 __global__ void __launch_bounds__(kGemmPThreads, 1)
 gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
@@ -724,6 +726,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
     const int wq = warp - 8;
     int t = 0;
     float rlo = INFINITY, rhi = -INFINITY;   // range of everything this thread stores, flushed once
+    float* stg = reinterpret_cast<float*>(tiles_ptr + kStages3 * kStageBytes3) + wq * (32 * kStgPitch);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
       const int mt = tile % m_tiles, nt = (tile / m_tiles) % n_tiles, z = tile / (m_tiles * n_tiles);
       const int m0 = mt * kBM, n0 = nt * kBN;
@@ -753,18 +756,42 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&s_acc_empty[buf]))
                          : "memory");
         }
-        if (m < p.M) {
-          const int nc = n0 + c * 32;
-          float v[32];
+        const int nc = n0 + c * 32;
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = (__uint_as_float(r[j]) + __uint_as_float(r2[j])) + bias_m;
-            if (p.relu) v[j] = fmaxf(v[j], 0.f);
-            if (nc + j < p.N) {
-              rlo = fminf(rlo, v[j]);
-              rhi = fmaxf(rhi, v[j]);
-            }
+        for (int j = 0; j < 32; ++j) {
+          v[j] = (__uint_as_float(r[j]) + __uint_as_float(r2[j])) + bias_m;
+          if (p.relu) v[j] = fmaxf(v[j], 0.f);
+          if (m < p.M && nc + j < p.N) {
+            rlo = fminf(rlo, v[j]);
+            rhi = fmaxf(rhi, v[j]);
           }
+        }
+        // A thread holds 32 consecutive pixels of ONE output row, so a direct 16-byte store touches 32
+        // rows x 16 bytes per instruction (half sectors). For full chunks the 32 x 32 block goes through a
+        // padded shared-memory tile and is written as 4 rows x 128 contiguous bytes per instruction.
+        float* blk = p.D + (long long)z * p.d_batch_stride + (long long)(m0 + wq * 32) * p.ldd + nc;
+        float* blk2 = p.D2 ? p.D2 + (blk - p.D) : nullptr;
+        const bool full = (m0 + wq * 32 + 32 <= p.M) && (nc + 32 <= p.N) && ((p.ldd & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(blk) & 15u) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(blk2) & 15u) == 0);
+        if (full) {
+          __syncwarp();   // the previous chunk's reads of the staging tile are done
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(stg + lane * kStgPitch + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          __syncwarp();
+          const int rr = lane >> 3, cc = (lane & 7) * 4;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int row = 4 * q + rr;
+            const float4 t = *reinterpret_cast<const float4*>(stg + row * kStgPitch + cc);
+            *reinterpret_cast<float4*>(blk + (long long)row * p.ldd + cc) = t;
+            if (blk2)
+              *reinterpret_cast<float4*>(blk2 + (long long)row * p.ldd + cc) =
+                  make_float4(relu_keep_nan(t.x), relu_keep_nan(t.y), relu_keep_nan(t.z), relu_keep_nan(t.w));
+          }
+        } else if (m < p.M) {
           float* dst = drow + nc;
           float* dst2 = p.D2 ? p.D2 + (drow - p.D) + nc : nullptr;
           if (nc + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) &&
@@ -1590,14 +1617,14 @@ extern "C" int dpl_gemm_tf32x3(const float* d_a, const float* d_a_lo, int a_majo
     static bool attr_done_p = false;
     if (!attr_done_p) {
       int e = cuda_status(cudaFuncSetAttribute(gemm_tf32x3_persistent_kernel,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + kStgBytes)),
                           "cudaFuncSetAttribute(gemm_tf32x3_persistent_kernel)");
       if (e) return e;
       attr_done_p = true;
     }
     const long long total = (long long)grid.x * grid.y * grid.z;
     const unsigned ctas = (unsigned)(total < sm_count() ? total : sm_count());
-    gemm_tf32x3_persistent_kernel<<<ctas, kGemmPThreads, smem, s>>>(tmA, tmAlo, tmB, p);
+    gemm_tf32x3_persistent_kernel<<<ctas, kGemmPThreads, smem + kStgBytes, s>>>(tmA, tmAlo, tmB, p);
     DPL_LAUNCH_CHECK("gemm_tf32x3_persistent_kernel");
     return 0;
   }
