@@ -324,7 +324,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // reference's CPU path (clip values are compared at 1e-5).
 constexpr int kStages3 = 3;
 constexpr int kStageBytes3 = 4 * kTileBytes;        // A_hi | A_lo | B | B_lo
-constexpr int kGemm3Threads = 256;
+#ifndef DPL_XFORM_WARPS
+#define DPL_XFORM_WARPS 4   // 8 measured: no change (the transform is not the critical path)
+#endif
+constexpr int kXformWarps = DPL_XFORM_WARPS;        // transform warps of the one-tile-per-CTA 3xTF32 kernels
+constexpr int kXformThreads = 32 * kXformWarps;
+constexpr int kGemm3Threads = 128 + kXformThreads;
 constexpr int kTmemCols3 = 512;                     // three 128-column accumulators (power of two)
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -365,7 +370,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages3; ++s) {
       bar_init(smem_addr(&s_full[s]), 1);
-      bar_init(smem_addr(&s_ready[s]), 4);   // one arrival per transform warp
+      bar_init(smem_addr(&s_ready[s]), kXformWarps);   // one arrival per transform warp
       bar_init(smem_addr(&s_empty[s]), 1);
     }
     bar_init(smem_addr(&s_tmem_full), 1);
@@ -480,9 +485,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const float4* src = reinterpret_cast<const float4*>(tiles_ptr + s * kStageBytes3 + 2 * kTileBytes);
       float4* dst = reinterpret_cast<float4*>(tiles_ptr + s * kStageBytes3 + 3 * kTileBytes);
 #pragma unroll
-      for (int j = 0; j < kTileBytes / 16 / 128; ++j) {
-        const float4 v = src[t + j * 128];
-        dst[t + j * 128] = make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z),
+      for (int j = 0; j < kTileBytes / 16 / kXformThreads; ++j) {
+        const float4 v = src[t + j * kXformThreads];
+        dst[t + j * kXformThreads] = make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z),
                                        tf32_residual(v.w));
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (MMA)
@@ -892,7 +897,7 @@ conv_taps_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages3; ++s) {
       bar_init(smem_addr(&s_full[s]), 1);
-      bar_init(smem_addr(&s_ready[s]), 4);
+      bar_init(smem_addr(&s_ready[s]), kXformWarps);
       bar_init(smem_addr(&s_empty[s]), 1);
     }
     bar_init(smem_addr(&s_tmem_full), 1);
@@ -986,9 +991,9 @@ conv_taps_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       const float4* src = reinterpret_cast<const float4*>(tiles_ptr + s * kStageBytes3);
       float4* dst = reinterpret_cast<float4*>(tiles_ptr + s * kStageBytes3 + kTileBytes);
 #pragma unroll
-      for (int j = 0; j < kTileBytes / 16 / 128; ++j) {
-        const float4 v = src[t + j * 128];
-        dst[t + j * 128] = make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z),
+      for (int j = 0; j < kTileBytes / 16 / kXformThreads; ++j) {
+        const float4 v = src[t + j * kXformThreads];
+        dst[t + j * kXformThreads] = make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z),
                                        tf32_residual(v.w));
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
