@@ -67,10 +67,10 @@ class Engine:
         # the channel-major persistent tile on ResNet-50's shapes, so opt-in
         self.conv1x1_px = os.environ.get("DPL_ENGINE_CONV1X1_PX", "0") == "1"
         self.native_ops = os.environ.get("DPL_ENGINE_NATIVE_OPS", "1") != "0"
-        # Relu blob written by the Conv epilogue (second store stream). Measured on B200 at batch 64: the
-        # Relu pass disappears (0.46 -> 0.07 ms) but the non-overlapped epilogues grow by more
-        # (convolutions 6.07 -> 6.66 ms), so it stays off until the epilogue overlaps the main loop.
-        self.fuse_conv_relu = os.environ.get("DPL_ENGINE_FUSE_CONV_RELU", "0") == "1"
+        # Relu blob written by the Conv epilogue (second store stream). Measured on B200, hist job: a loss
+        # with the row-per-thread epilogue stores (convolutions 6.07 -> 6.66 ms per 64 images), a small gain
+        # (7820 -> 7890 images/s) once the persistent 1x1 tile stores through its shared-memory transpose.
+        self.fuse_conv_relu = os.environ.get("DPL_ENGINE_FUSE_CONV_RELU", "1") != "0"
         self.arena = None          # kernels.BlobArena: where node outputs are allocated
         self.refresh_initializers()
         self.nodes = list(onnx_graph.model.graph.nodes)
