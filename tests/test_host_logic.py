@@ -126,3 +126,47 @@ def test_weight_calibration_we_recalibrates_like_the_reference(mname, monkeypatc
         assert np.allclose([act2[k][0], act2[k][1]], v, rtol=1e-5, atol=1e-6), (k, act2[k], v)
     changed = [k for k in act if not np.allclose(act[k], act2[k], rtol=1e-4, atol=1e-6)]
     assert changed      # equalisation moved the ranges of the blobs between the paired layers
+
+
+def test_blob_arena_bump_allocation():
+    """One slab, 256-byte aligned float32 views, MemoryError when exhausted (the engine then falls back
+    to torch's allocator), reset() recycles the slab."""
+    import torch
+    from dipoorlet_b200.kernels import BlobArena
+    arena = BlobArena(4096, torch.device("cpu"))
+    a = arena.alloc((3, 5))            # 60 bytes -> next offset 256
+    b = arena.alloc((64,))
+    assert a.dtype == torch.float32 and a.shape == (3, 5) and b.shape == (64,)
+    assert (b.data_ptr() - a.data_ptr()) == 256 and arena.off == 512
+    a.fill_(1.0)
+    b.fill_(2.0)
+    assert float(a.sum()) == 15.0 and float(b.sum()) == 128.0     # views do not overlap
+    with pytest.raises(MemoryError):
+        arena.alloc((1024,))
+    arena.reset()
+    c = arena.alloc((4,))
+    assert c.data_ptr() == a.data_ptr()
+
+
+def test_range_sink_cover_and_uncover(cpu_product):
+    """Bookkeeping of the fused range statistics: a kernel that registers an output covers it; a node
+    whose fused kernel refuses (GemmUnsupported) gives its outputs - and the Relu fused behind it -
+    back to K1."""
+    import torch
+    from dipoorlet_b200.engine import Engine, RangeSink
+    graph, model, images, args = cpu_product
+    eng = Engine(graph, "cpu", _unit_test_cpu=True)
+    names = eng.blob_names()
+    sink = RangeSink(torch.zeros(len(names)), torch.zeros(len(names)), names)
+    eng._stats = sink
+    conv = next(n for n in eng.nodes if n.op_type == "Conv" and eng._fusable_relu(n) is not None)
+    relu = eng._fusable_relu(conv)
+    bmin, bmax, idx = eng._rng(conv.output[0])
+    assert idx == names.index(conv.output[0]) and bmin is sink.blob_min
+    assert eng._rng_relu(conv)[2] == names.index(relu.output[0])
+    assert sink.covered == {conv.output[0], relu.output[0]}
+    eng._uncover(conv)
+    assert sink.covered == set()
+    assert eng._rng("not a blob") is None
+    eng._stats = None
+    assert eng._rng(conv.output[0]) is None
