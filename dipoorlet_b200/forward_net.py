@@ -146,6 +146,7 @@ class CalibrationSession:
         self._stats_stream = None
         self._slot_busy = [None, None]
         self._slot = 0
+        self._keep_now = False      # this pass keeps its blobs resident (set by run_minmax)
         self.arena = None
         f32 = dict(dtype=torch.float32, device=dev)
         self.blob_min = torch.full((self.n_stats,), float("inf"), **f32)
@@ -188,7 +189,7 @@ class CalibrationSession:
         else one batch, recycled (stream order makes the reuse safe)."""
         if self.device.type != "cuda":
             return
-        if self.keep_resident:
+        if self._keep_now:
             need = sum(self._batch_bytes(b1 - b0) for b0, b1 in ranges)
         else:
             # two batch-sized halves, used alternately: the statistics pass of batch i runs on a side
@@ -250,7 +251,7 @@ class CalibrationSession:
         for i, (b0, b1) in enumerate(ranges):
             feeds, ev = nxt
             main.wait_event(ev)
-            if not self.keep_resident:
+            if not self._keep_now:
                 self.arena.off = (i & 1) * self._half
                 if self._slot_busy[i & 1] is not None:
                     main.wait_event(self._slot_busy[i & 1])
@@ -272,7 +273,7 @@ class CalibrationSession:
             yield b0 - self.st, b1 - self.st, K.BlobBatch([blobs[n] for n in self.names])
 
     # -- pass 1: min / max (+ moments for OCTAV) ------------------------------------
-    def run_minmax(self, moments=False, octav_k=None, per_image=True):
+    def run_minmax(self, moments=False, octav_k=None, per_image=True, keep_for_hist=None):
         """Pass 1. per_image=False (the minmax / hist calibrators, which only use the range over all
         images, basic_algorithm.py:20-21,33-36): the forward's streaming kernels fold min / max of the
         blobs they write into blob_min / blob_max themselves, and K1 reads only the remaining blobs
@@ -282,6 +283,9 @@ class CalibrationSession:
         6201 without - the forward's kernels lose more to the contention than the hidden K1 pass saves -
         so the default keeps everything on one stream."""
         n, dev = self.n_local, self.device
+        # the blobs stay resident only when a histogram pass will read them again (keep_for_hist=False: the
+        # minmax / mse calibrators, which must not take a 110 GB slab for nothing)
+        self._keep_now = bool(self.keep_resident and octav_k is None and keep_for_hist is not False)
         fused = (not per_image and not moments and octav_k is None and dev.type == "cuda"
                  and os.environ.get("DPL_FUSED_RANGE", "1") != "0")
         if fused:
@@ -293,7 +297,7 @@ class CalibrationSession:
             self.seg_nnz = torch.empty((self.n_stats, n), dtype=torch.int64, device=dev)
         if octav_k is not None:
             self.seg_s = torch.empty((self.n_stats, n), dtype=torch.float32, device=dev)
-        keep = [] if (self.keep_resident and octav_k is None) else None
+        keep = [] if self._keep_now else None
         overlap = dev.type == "cuda" and os.environ.get("DPL_STATS_OVERLAP", "0") == "1"
         main = torch.cuda.current_stream(dev) if dev.type == "cuda" else None
         if overlap and self._stats_stream is None:
@@ -318,7 +322,7 @@ class CalibrationSession:
                            ctas_per_sm=2 if side is not None else 0)
                 if octav_k is not None:
                     K.octav(batch, ssum, snnz, octav_k, s, workspace=self.ws)
-                if side is not None and not self.keep_resident:
+                if side is not None and not self._keep_now:
                     done = torch.cuda.Event()
                     done.record(side)
                     self._slot_busy[self._slot] = done
@@ -342,7 +346,7 @@ class CalibrationSession:
         dev = self.device
         self.seg_min = self.seg_max = None
         sink = RangeSink(self.blob_min, self.blob_max, self.names)
-        keep = [] if self.keep_resident else None
+        keep = [] if self._keep_now else None
         for lo, hi, batch in self.batches(sink=sink):
             if keep is not None:
                 keep.append((lo, hi, batch))
@@ -374,6 +378,7 @@ class CalibrationSession:
                 events.append((e0, e1, batch.elements * 4))
             del batch
         self.resident = None  # release the blobs
+        self._keep_now = False
         if self.keep_resident:
             self.arena = None
         dist_helper.allreduce_sum(self.counts)
@@ -406,6 +411,7 @@ def forward_get_minmax(onnx_graph, args):
     """-> {name: {'max': float32[n_local], 'min': float32[n_local]}} (forward_net.py:192-237);
     per-image values in image order, as arrays instead of lists of scalars."""
     sess = _session(onnx_graph, args, fresh=True)
+    # the blobs are kept for forward_get_hist (the reference's two-call sequence) when they fit
     sess.run_minmax()
     return sess.minmax_dict()
 

@@ -24,7 +24,7 @@ def _global_images(sess, t):
 def find_clip_val_minmax(onnx_graph, args, **kwargs):
     """[min over images, max over images] per blob (basic_algorithm.py:13-22)."""
     sess = fwd._session(onnx_graph, args, fresh=True)
-    sess.run_minmax(per_image=False)       # only the range over all images is used (:20-21)
+    sess.run_minmax(per_image=False, keep_for_hist=False)   # only the range over all images is used (:20-21)
     dist_helper.allreduce_minmax(sess.blob_min, sess.blob_max)
     lo, hi = sess.blob_min.cpu().numpy(), sess.blob_max.cpu().numpy()
     return {name: [lo[i], hi[i]] for i, name in enumerate(sess.names)}
