@@ -61,3 +61,45 @@ def test_engine_refuses_cpu():
     g = ONNXGraph(W.build_resnet50(blocks=[1], planes=(4,), stem=4, num_classes=3, image=16), "", "trt")
     with pytest.raises(RuntimeError):
         Engine(g, "cpu")
+
+
+def _prototypes():
+    """name -> list of C parameter type strings, parsed from the header."""
+    text = open(os.path.join(ROOT, "include", "dpl_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|size_t|const char\*)\s+(dpl_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+        protos[m.group(1)] = [] if params in ([""], ["void"]) else params
+    return protos
+
+
+def test_ctypes_signatures_match_the_header(dpl_built):
+    """Every prototype of include/dpl_b200.h against _lib.SIGNATURES: same number of parameters and the
+    same class of type at each position (pointer / 32-bit int / 64-bit int / float / double / size_t), so
+    that a changed C signature cannot silently shift the arguments of a ctypes call."""
+    from dipoorlet_b200 import _lib
+
+    def c_class(decl):
+        decl = re.sub(r"\b[a-zA-Z_][a-zA-Z0-9_]*$", "", decl.strip()).strip()   # drop the parameter name
+        if "*" in decl:
+            return "ptr"
+        base = decl.replace("const", "").replace("unsigned", "u").strip()
+        return {"int": "i32", "float": "f32", "double": "f64", "size_t": "size", "uint64_t": "i64", "long long": "i64",
+                "u long long": "i64", "int32_t": "i32", "uint32_t": "i32"}[base]
+
+    def ct_class(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+            return "ptr"
+        return {ctypes.c_int: "i32", ctypes.c_float: "f32", ctypes.c_double: "f64", ctypes.c_size_t: "size",
+                ctypes.c_uint64: "i64", ctypes.c_longlong: "i64"}[t]
+
+    protos = _prototypes()
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, params in protos.items():
+        _, argtypes = _lib.SIGNATURES[name]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for i, (decl, t) in enumerate(zip(params, argtypes)):
+            got, want = ct_class(t), c_class(decl)
+            # size_t and uint64_t are the same width on this ABI; both are accepted for either
+            assert got == want or {got, want} == {"size", "i64"}, (name, i, decl, t)
