@@ -170,3 +170,28 @@ def test_range_sink_cover_and_uncover(cpu_product):
     assert eng._rng("not a blob") is None
     eng._stats = None
     assert eng._rng(conv.output[0]) is None
+
+
+def test_cli_flags_are_the_references():
+    """Drop-in boundary: every flag of the reference CLI (dipoorlet/__main__.py:23-55, extracted by
+    oracle/gen_cli_flags.py) exists here with the same option strings, default, choices, action and
+    `required`; the only deviations are supersets (--bins parsed as int, Appendix C-1; extra flags)."""
+    from dipoorlet_b200.cli_args import build_parser
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cli_flags.json")))
+    assert len(gold) == 28
+    ours = {tuple(a.option_strings): a for a in build_parser()._actions}
+    for g in gold:
+        a = ours.get(tuple(g["names"]))
+        assert a is not None, g["names"]
+        assert a.default == g.get("default", False if g.get("action") == "store_true" else None), g["names"]
+        assert (list(a.choices) if a.choices else None) == g.get("choices"), g["names"]
+        assert a.required == g.get("required", False), g["names"]
+        if g.get("action") == "store_true":
+            assert a.nargs == 0 and a.const is True
+        if g["names"] == ["--bins"]:
+            assert a.type is int            # the reference leaves it a str and crashes when it is passed
+        else:
+            assert (a.type.__name__ if a.type else None) == g.get("type"), g["names"]
+        assert a.nargs == g.get("nargs", 0 if g.get("action") == "store_true" else None), g["names"]
+    extra = set(ours) - {tuple(g["names"]) for g in gold} - {("-h", "--help")}
+    assert extra == {("--calib_bs",), ("--resident",)}
