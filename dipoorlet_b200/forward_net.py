@@ -109,7 +109,7 @@ def _per_image_shape(onnx_graph, name):
     return shape[1:]
 
 
-def default_batch(onnx_graph, engine, budget_bytes=14 << 30, cap=128):
+def default_batch(onnx_graph, engine, budget_bytes=28 << 30, cap=256):
     per_img = 4 * sum(int(np.prod(onnx_graph.get_tensor_shape(n)[1:]))
                       for n in engine.blob_names() if n in onnx_graph.tensor_name_shape_map)
     return int(max(1, min(cap, budget_bytes // max(per_img, 1))))
@@ -163,13 +163,14 @@ class CalibrationSession:
             else bool(args.resident)
 
     def _fits_resident(self):
+        """The slab of a resident pass (every batch's blobs, exactly what _attach_arena will take) plus a
+        margin for the engine's weights / staging scratch and the statistics must fit in what is free now."""
         if self.device.type != "cuda":
             return False
-        per_img = 4 * sum(int(np.prod(self.g.get_tensor_shape(n)[1:])) for n in self.names
-                          if n in self.g.tensor_name_shape_map)
+        need = sum(self._batch_bytes(b1 - b0) for b0, b1 in self._ranges()) + (6 << 30)
         free, _ = torch.cuda.mem_get_info(self.device)
         reusable = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
-        return per_img * (self.n_local + 2 * self.batch_size) < 0.85 * (free + reusable)
+        return need < 0.92 * (free + reusable)
 
     def _ranges(self):
         return [(b0, min(b0 + self.batch_size, self.ed)) for b0 in range(self.st, self.ed, self.batch_size)]
