@@ -120,3 +120,32 @@ def test_oracle_qdq_forward_equals_reference(mname, tmp_path):
         kind, t = key.split("|", 1)
         src = fp[t] if kind == "fp" else q[t if t in q else t + "_dq"]
         assert np.array_equal(np.stack(src), gold[key]), key
+
+
+def test_quant_params_equal_reference_on_all_platform_parameter_sets():
+    """get_qnode_by_param (quantize.py:111-194) against the reference's own outputs on 208 seeded cases:
+    the weight and activation parameter sets of all eight platforms (symmetric / asymmetric, per-tensor /
+    per-channel, log_scale, dynamic_sym), scalar and per-channel ranges incl. zero ranges, one-sided ranges
+    and all-zero channels (tests/golden/qparam_fuzz.json, oracle/gen_golden_qparams.py). Scales must be the
+    same float32 bit patterns, zero points / q limits the same integers, dtypes and axis attributes equal;
+    and the product's platform table must carry the same parameter sets."""
+    from dipoorlet_b200.platform_settings import platform_setting_table
+    from dipoorlet_b200.quantize import get_qnode_by_param
+    gold = json.load(open(os.path.join(GOLD, "qparam_fuzz.json")))
+    for platform, sets in gold["params"].items():
+        for key, want in sets.items():
+            assert platform_setting_table[platform][key] == want, (platform, key)
+    assert len(gold["rows"]) == 208
+    for row in gold["rows"]:
+        param = gold["params"][row["platform"]][row["key"]]
+        rr = [np.array(v, dtype=np.float64) if isinstance(v, list) else np.float64(v) for v in row["range"]]
+        q_nodes, q_min, q_max = get_qnode_by_param(param, "t", row["shape"], copy.deepcopy(rr))
+        inits = dict(q_nodes.initializer)
+        scale, zp = np.asarray(inits["t_scale"]), np.asarray(inits["t_zero_point"])
+        tag = (row["platform"], row["key"], row["range"])
+        assert str(scale.dtype) == row["scale_dtype"] and str(zp.dtype) == row["zp_dtype"], tag
+        assert np.array_equal(scale.reshape(-1), np.asarray(row["scale"], dtype=np.float32)), tag
+        assert zp.reshape(-1).astype(int).tolist() == row["zero_point"], tag
+        assert np.asarray(q_min).reshape(-1).astype(int).tolist() == row["q_min"], tag
+        assert np.asarray(q_max).reshape(-1).astype(int).tolist() == row["q_max"], tag
+        assert [n.attrs.get("axis") for n in q_nodes.node] == row["axis"], tag
