@@ -149,3 +149,35 @@ def test_quant_params_equal_reference_on_all_platform_parameter_sets():
         assert np.asarray(q_min).reshape(-1).astype(int).tolist() == row["q_min"], tag
         assert np.asarray(q_max).reshape(-1).astype(int).tolist() == row["q_max"], tag
         assert [n.attrs.get("axis") for n in q_nodes.node] == row["axis"], tag
+
+
+@pytest.mark.parametrize("mname", MODELS)
+@pytest.mark.parametrize("platform", ["trt", "stpu", "magicmind", "rv", "atlas", "snpe", "ti", "imx"])
+def test_quant_graph_equals_reference_on_every_platform(mname, platform, tmp_path):
+    """The Q/DQ rewrite (quantize.py:20-108) for each of the eight deploy platforms of the reference's table:
+    same quantised-node list, node-for-node identical graph (names, wiring, axis attributes), same network
+    outputs (platforms that quantise them) and bit-identical scale / zero-point initializers
+    (tests/golden/*/quant_graph_platforms.json, oracle/gen_golden_quant_graphs.py)."""
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.quantize import quant_graph
+    d, model, images, calib = _load(mname)
+    want = json.load(open(os.path.join(d, "quant_graph_platforms.json")))[platform]
+    graph = ONNXGraph(model, str(tmp_path), platform)
+    args = make_args(input_dir="unused", data_num=8, deploy=platform, output_dir=str(tmp_path))
+    gold_w = np.load(os.path.join(d, "weight_clip.npz"))
+    clip = {k: [np.float64(v[0]), np.float64(v[1])] for k, v in calib["minmax"]["act"].items()}
+    for key in gold_w.files:
+        name, i = key.rsplit("|", 1)
+        clip.setdefault(name, [None, None])[int(i)] = gold_w[key]
+    gq, qlist = quant_graph(graph, copy.deepcopy(clip), args)
+    assert [n.name for n in qlist] == want["quant_node_list"]
+    got_nodes = [[n.op_type, n.name, list(n.input), list(n.output),
+                  {k: v for k, v in n.attrs.items() if k == "axis"}] for n in gq.graph.node]
+    assert got_nodes == want["nodes"]
+    assert list(gq.network_outputs) == want["network_outputs"]
+    inits = gq.model.graph.initializers
+    assert sorted(k for k in inits if k.endswith("_scale") or k.endswith("_zero_point")) == sorted(want["qparams"])
+    for name, (dtype, vals) in want["qparams"].items():
+        assert str(inits[name].dtype) == dtype, name
+        assert np.array_equal(np.asarray(inits[name], dtype=np.float64).reshape(-1), np.asarray(vals)), name
