@@ -181,3 +181,47 @@ def test_quant_graph_equals_reference_on_every_platform(mname, platform, tmp_pat
     for name, (dtype, vals) in want["qparams"].items():
         assert str(inits[name].dtype) == dtype, name
         assert np.array_equal(np.asarray(inits[name], dtype=np.float64).reshape(-1), np.asarray(vals)), name
+
+
+def test_clip_and_profiling_files_equal_reference_over_three_ranks(tmp_path):
+    """The on-disk boundary (utils.py:313-412): per-rank act / weight clip files, the rank-0 combine
+    (min / max for minmax, mean of clips otherwise), the reload types (np.float64 scalars; per-channel arrays
+    only on per-channel platforms) and the per-rank profiling files with their mean / min combine - every
+    file byte for byte, every value and type equal to what the reference produced on the same 3-rank inputs
+    (tests/golden/persistence.json, oracle/gen_golden_persistence.py)."""
+    import types
+    from dipoorlet_b200 import utils as U
+    gold = json.load(open(os.path.join(GOLD, "persistence.json")))
+    ranks = gold["ranks"]
+    for case, want in gold["cases"].items():
+        deploy, algo = case.split("|")
+        out = tmp_path / case.replace("|", "_")
+        out.mkdir()
+        args = types.SimpleNamespace(output_dir=str(out), act_quant=algo, deploy=deploy, model_type=None)
+        for r in range(ranks):
+            act = {k: [np.float32(v[0]), np.float32(v[1])] for k, v in gold["act_ranks"][r].items()}
+            weight = {k: [np.asarray(v[0], np.float32), np.asarray(v[1], np.float32)] for k, v in gold["weight"].items()}
+            U.save_clip_val(act, weight, args, act_fname=f"act_clip_val.json.rank{r}",
+                            weight_fname=f"weight_clip_val.json.rank{r}")
+        U.reduce_clip_val(ranks, args)
+        act, w = U.load_clip_val(args)
+        files = {f: open(os.path.join(str(out), f)).read() for f in sorted(os.listdir(str(out)))}
+        assert sorted(files) == sorted(want["files"]), case
+        for f in files:
+            assert files[f] == want["files"][f], (case, f)
+        assert list(act) == list(want["act"])
+        for k, (lo, hi, tname) in want["act"].items():
+            assert float(act[k][0]) == lo and float(act[k][1]) == hi and type(act[k][0]).__name__ == tname, (case, k)
+        for k, (lo, hi, tname, shape) in want["weight"].items():
+            assert np.asarray(w[k][0]).tolist() == lo and np.asarray(w[k][1]).tolist() == hi, (case, k)
+            assert type(w[k][0]).__name__ == tname and list(np.asarray(w[k][0]).shape) == shape, (case, k)
+    out = tmp_path / "prof"
+    out.mkdir()
+    args = types.SimpleNamespace(output_dir=str(out), model_type=None)
+    for r in range(ranks):
+        U.save_profiling_res(dict(gold["layer_ranks"][r]), {k: list(v) for k, v in gold["model_ranks"][r].items()},
+                             args, rank=r)
+    files = {f: open(os.path.join(str(out), f)).read() for f in sorted(os.listdir(str(out)))}
+    assert files == gold["profiling"]["files"]
+    layer, model = U.reduce_profiling_res(ranks, args)
+    assert layer == gold["profiling"]["layer"] and model == gold["profiling"]["model"]
