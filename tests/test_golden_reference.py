@@ -225,3 +225,26 @@ def test_clip_and_profiling_files_equal_reference_over_three_ranks(tmp_path):
     assert files == gold["profiling"]["files"]
     layer, model = U.reduce_profiling_res(ranks, args)
     assert layer == gold["profiling"]["layer"] and model == gold["profiling"]["model"]
+
+
+@pytest.mark.parametrize("mname", MODELS)
+def test_graph_ir_equals_reference(mname, tmp_path):
+    """ONNXGraph, the first argument of every registry function (utils.py:22-250): node names in order,
+    network inputs / outputs, initializer names, tensor shapes, producer and consumer maps as the
+    reference's own class reports them (tests/golden/*/graph_api.json, oracle/gen_golden_graph_api.py)."""
+    from dipoorlet_b200.graph import ONNXGraph
+    d, model, images, calib = _load(mname)
+    want = json.load(open(os.path.join(d, "graph_api.json")))
+    g = ONNXGraph(model, str(tmp_path), "trt")
+    assert [[n.op_type, n.name, list(n.input), list(n.output)] for n in g.graph.node] == want["nodes"]
+    assert list(g.network_inputs) == want["network_inputs"]
+    assert list(g.network_outputs) == want["network_outputs"]
+    assert sorted(g.initializer.keys()) == want["initializers"]
+    for t, shape in want["shapes"].items():
+        assert [int(v) for v in g.get_tensor_shape(t)] == shape, t
+    for t, p in want["producer"].items():
+        got = g.get_tensor_producer(t)
+        assert (got if isinstance(got, str) else got.name) == p, t
+    for t, cons in want["consumer"].items():
+        got = [(c if isinstance(c, str) else c.name) for c in g.get_tensor_consumer(t)]
+        assert got == cons, t
