@@ -274,7 +274,7 @@ class CalibrationSession:
             yield b0 - self.st, b1 - self.st, K.BlobBatch([blobs[n] for n in self.names])
 
     # -- pass 1: min / max (+ moments for OCTAV) ------------------------------------
-    def run_minmax(self, moments=False, octav_k=None, per_image=True, keep_for_hist=None):
+    def run_minmax(self, moments=False, octav_k=None, per_image=True, keep_for_hist=None, octav_k_zero_min=None):
         """Pass 1. per_image=False (the minmax / hist calibrators, which only use the range over all
         images, basic_algorithm.py:20-21,33-36): the forward's streaming kernels fold min / max of the
         blobs they write into blob_min / blob_max themselves, and K1 reads only the remaining blobs
@@ -323,6 +323,13 @@ class CalibrationSession:
                            ctas_per_sm=2 if side is not None else 0)
                 if octav_k is not None:
                     K.octav(batch, ssum, snnz, octav_k, s, workspace=self.ws)
+                    if octav_k_zero_min is not None:
+                        # 'dynamic_sym' platforms (forward_net.py:318-322): a segment whose minimum is 0 gains a
+                        # bit (unsigned = 4). The constant is per launch, so the fixed point is evaluated with both
+                        # and each segment takes the one its own minimum selects.
+                        s_alt = torch.empty_like(s)
+                        K.octav(batch, ssum, snnz, octav_k_zero_min, s_alt, workspace=self.ws)
+                        s = torch.where(smin.abs() < 1e-6, s_alt, s)
                 if side is not None and not self._keep_now:
                     done = torch.cuda.Event()
                     done.record(side)
@@ -435,10 +442,9 @@ def forward_get_hist(onnx_graph, stats_min_max, args):
 def forward_net_octav(onnx_graph, args):
     """-> {name: {'optimal_s': float32[n_local], 'min': ..., 'max': ...}} (forward_net.py:284-342)."""
     sess = _session(onnx_graph, args, fresh=True)
-    if "dynamic_sym" in platform_setting_table[args.deploy]["qi_params"]:
-        raise NotImplementedError("'mse' calibration with a dynamic_sym platform (unsigned = 4 "
-                                  "per blob, forward_net.py:319-322) is outside the trt hot path")
-    sess.run_minmax(moments=True, octav_k=1 / (4 ** 8) / 3 / 1)
+    dyn = "dynamic_sym" in platform_setting_table[args.deploy]["qi_params"]
+    sess.run_minmax(moments=True, octav_k=1 / (4 ** 8) / 3 / 1,
+                    octav_k_zero_min=(1 / (4 ** 8) / 3 / 4) if dyn else None)
     s, mx, mn = sess.seg_s.cpu().numpy(), sess.seg_max.cpu().numpy(), sess.seg_min.cpu().numpy()
     return {name: {"optimal_s": s[i], "min": mn[i], "max": mx[i]} for i, name in enumerate(sess.names)}
 

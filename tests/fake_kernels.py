@@ -68,5 +68,6 @@ def hist_percentile(counts, bins, threshold, data_max, blob_min, blob_max, clip,
 
 
 def octav(batch, seg_abssum, seg_nnz, k_const, out_s, out_iters=None, max_iter=20, workspace=None):
+    unsigned = int(round((1 / 4 ** 8 / 3) / k_const))       # k = 1 / 4**8 / 3 / unsigned (forward_net.py:319-328)
     for k, (b, x) in enumerate(_segs(batch)):
-        out_s[k] = float(O.octav_stats({"x": [x]})["x"]["optimal_s"][0])
+        out_s[k] = float(O.octav_stats({"x": [x]}, unsigned_of=lambda m: unsigned)["x"]["optimal_s"][0])

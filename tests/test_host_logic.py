@@ -195,3 +195,37 @@ def test_cli_flags_are_the_references():
         assert a.nargs == g.get("nargs", 0 if g.get("action") == "store_true" else None), g["names"]
     extra = set(ours) - {tuple(g["names"]) for g in gold} - {("-h", "--help")}
     assert extra == {("--calib_bs",), ("--resident",)}
+
+
+def test_mse_on_a_dynamic_sym_platform(monkeypatch, tmp_path):
+    """'ti' declares dynamic_sym for activations: a blob of an image whose minimum is 0 (post-ReLU blobs)
+    runs the OCTAV update with unsigned = 4, all others with 1 (forward_net.py:318-328). The session
+    evaluates both constants and selects per segment; result == the oracle's per-image rule."""
+    import torch
+    from dipoorlet_b200 import forward_net as fwd
+    from dipoorlet_b200 import workloads as W
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.engine import Engine
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.tensor_cali import tensor_calibration
+    from oracle import stats as O
+    monkeypatch.setattr(fwd, "K", fake_kernels)
+    fwd._SESSIONS.clear()
+    model = W.build_resnet50(blocks=[1, 1], planes=(4, 8), stem=8, num_classes=5, image=32)
+    graph = ONNXGraph(model, str(tmp_path), "ti")
+    images = W.synthetic_images(5, (3, 32, 32), seed=8)
+    W.write_input_dir(images, str(tmp_path / "data"), "input")
+    args = make_args(input_dir=str(tmp_path / "data"), data_num=5, deploy="ti", act_quant="mse",
+                     output_dir=str(tmp_path), calib_bs=2, _test_device="cpu")
+    act, _ = tensor_calibration(graph, args)
+    eng = Engine(graph, "cpu", _unit_test_cpu=True)
+    blobs = eng.run({"input": torch.from_numpy(images[:, 0])}, want="all")
+    blobs = {k: [v[i].numpy() for i in range(5)] for k, v in blobs.items()}
+    rule = lambda m: 4 if np.abs(m - 0) < 1e-6 else 1      # noqa: E731
+    ref = O.clip_octav(O.octav_stats(blobs, unsigned_of=rule))
+    plain = O.clip_octav(O.octav_stats(blobs))
+    assert list(act) == list(ref)
+    for k in ref:
+        assert np.allclose(act[k], ref[k], rtol=2e-6, atol=1e-7), (k, act[k], ref[k])
+    # the rule matters: post-ReLU blobs differ from the unsigned = 1 result
+    assert any(not np.allclose(ref[k], plain[k], rtol=1e-4) for k in ref)
