@@ -248,3 +248,25 @@ def test_graph_ir_equals_reference(mname, tmp_path):
     for t, cons in want["consumer"].items():
         got = [(c if isinstance(c, str) else c.name) for c in g.get_tensor_consumer(t)]
         assert got == cons, t
+
+
+@pytest.mark.parametrize("mname", MODELS)
+@pytest.mark.parametrize("platform", ["atlas", "imx", "magicmind", "snpe", "ti"])
+def test_vendor_deploy_files_byte_identical(mname, platform, tmp_path):
+    """to_deploy for the five small vendor formats: fed the clip-value files the reference wrote, the
+    product reloads them (load_clip_val: scalar vs per-channel weights per platform) and must write the same
+    deploy files byte for byte (tests/golden/*/deploy_vendors.json, oracle/gen_golden_deploy.py)."""
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.deploy import to_deploy
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.utils import load_clip_val
+    d, model, images, calib = _load(mname)
+    gold = json.load(open(os.path.join(d, "deploy_vendors.json")))[platform]
+    (tmp_path / "act_clip_val.json").write_text(gold["act_clip_val"])
+    (tmp_path / "weight_clip_val.json").write_text(gold["weight_clip_val"])
+    graph = ONNXGraph(model, str(tmp_path), platform)
+    args = make_args(input_dir="unused", data_num=8, deploy=platform, output_dir=str(tmp_path))
+    act, weight = load_clip_val(args)
+    to_deploy(graph, act, weight, args)
+    for fname, text in gold["files"].items():
+        assert (tmp_path / fname).read_text() == text, fname
