@@ -136,6 +136,16 @@ class Engine:
             if relu is not None:
                 st.covered.discard(relu.output[0])
 
+    def _fallback(self, node):
+        """A libdpl_b200 kernel refused this node's operands (alignment / shape): say so once, route the node
+        to the next path for the rest of the run and give its blobs' range statistics back to K1."""
+        if node.name not in self._tc_off:
+            from .utils import logger
+            logger.warning("engine: %s (%s) falls back from its libdpl_b200 kernel: %s"
+                           % (node.name, node.op_type, K.lib().dpl_last_error().decode("utf-8", "replace")))
+        self._tc_off.add(node.name)
+        self._uncover(node)
+
     def _rng_relu(self, node):
         relu = self._fusable_relu(node)
         return self._rng(relu.output[0]) if relu is not None else None
@@ -330,8 +340,7 @@ class Engine:
                     self._publish_relu(node, r, env)
                     return [y]
                 except K.GemmUnsupported:
-                    self._tc_off.add(node.name)
-                    self._uncover(node)
+                    self._fallback(node)
             taps_cfg = self._tc_conv_taps(node, x, w, stride, dil, lo, hi)
             if taps_cfg is not None:
                 try:
@@ -349,8 +358,7 @@ class Engine:
                     self._publish_relu(node, r, env)
                     return [y]
                 except K.GemmUnsupported:
-                    self._tc_off.add(node.name)
-                    self._uncover(node)
+                    self._fallback(node)
             if (self.stem_direct and x.is_cuda and node.name not in self._tc_off and w.dim() == 4 and x.dim() == 4
                     and x.is_contiguous() and w.is_contiguous() and a.get("group", 1) == x.shape[1] == w.shape[0]
                     and w.shape[1] == 1 and x.shape[1] > 1 and list(dil) == [1, 1] and sym and lo[0] == lo[1]
@@ -362,8 +370,7 @@ class Engine:
                     return [K.dwconv2d_forward(x, w, b, int(stride[0]), int(lo[0]), out=out,
                                                rng=self._rng(node.output[0]))]
                 except K.GemmUnsupported:
-                    self._tc_off.add(node.name)
-                    self._uncover(node)
+                    self._fallback(node)
             if (self.stem_direct and x.is_cuda and node.name not in self._tc_off and w.dim() == 4 and x.dim() == 4
                     and x.is_contiguous() and w.is_contiguous() and a.get("group", 1) == 1 and list(dil) == [1, 1]
                     and sym and lo[0] == lo[1] and stride[0] == stride[1] and w.shape[2] == w.shape[3]
@@ -379,8 +386,7 @@ class Engine:
                     self._publish_relu(node, r, env)
                     return [y]
                 except K.GemmUnsupported:
-                    self._tc_off.add(node.name)
-                    self._uncover(node)
+                    self._fallback(node)
             if (self.stem_im2col and self.tensor_cores and x.is_cuda and node.name not in self._tc_off and w.dim() == 4
                     and x.is_contiguous() and a.get("group", 1) == 1 and list(dil) == [1, 1] and sym
                     and lo[0] == lo[1] and stride[0] == stride[1] and x.shape[1] < 16
@@ -403,8 +409,7 @@ class Engine:
                     self._publish_relu(node, r, env)
                     return [y]
                 except K.GemmUnsupported:
-                    self._tc_off.add(node.name)
-                    self._uncover(node)
+                    self._fallback(node)
             if not sym:
                 x = F.pad(x, [p for i in reversed(range(nd)) for p in (lo[i], hi[i])])
                 lo = [0] * nd
@@ -492,8 +497,7 @@ class Engine:
                         return [K.linear_forward_x3(x, w, None, c, out=self._new((x.shape[0], w.shape[0]), x),
                                                     rng=self._rng(node.output[0]))]
                     except K.GemmUnsupported:
-                        self._tc_off.add(node.name)
-                        self._uncover(node)
+                        self._fallback(node)
                 return [F.linear(x, w, c)]
             y = alpha * (x @ (w.t() if a.get("transB", 0) else w))
             return [y if c is None else y + beta * c]

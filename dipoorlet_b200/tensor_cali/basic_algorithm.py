@@ -20,6 +20,13 @@ def _global_images(sess, t):
     return dist_helper.allgather_images(t).cpu().numpy()
 
 
+def _release(sess):
+    """The calibrator is done with the blobs: hand the slab back before the weight transforms and the
+    profiling allocate their activation caches (the statistics stay on the session)."""
+    sess.resident = None
+    sess.arena = None
+
+
 @tensor_cali_dispatcher.register('minmax')
 def find_clip_val_minmax(onnx_graph, args, **kwargs):
     """[min over images, max over images] per blob (basic_algorithm.py:13-22)."""
@@ -27,6 +34,7 @@ def find_clip_val_minmax(onnx_graph, args, **kwargs):
     sess.run_minmax(per_image=False, keep_for_hist=False)   # only the range over all images is used (:20-21)
     dist_helper.allreduce_minmax(sess.blob_min, sess.blob_max)
     lo, hi = sess.blob_min.cpu().numpy(), sess.blob_max.cpu().numpy()
+    _release(sess)
     return {name: [lo[i], hi[i]] for i, name in enumerate(sess.names)}
 
 
@@ -51,6 +59,7 @@ def find_clip_val_hist(onnx_graph, args, store_stats=None, **kwargs):
         sess.run_hist(bins)
     clip, sel = sess.percentile_clip(bins, args.threshold)
     clip = clip.cpu().numpy()
+    _release(sess)
     return {name: [clip[i, 0], clip[i, 1]] for i, name in enumerate(sess.names)}
 
 
@@ -63,6 +72,7 @@ def find_clip_val_octav(onnx_graph, args, **kwargs):
     s = _global_images(sess, sess.seg_s)
     mx = _global_images(sess, sess.seg_max)
     mn = _global_images(sess, sess.seg_min)
+    _release(sess)
     clip_val = {}
     for i, name in enumerate(sess.names):
         data_max, data_min = mx[i].max(), mn[i].min()
