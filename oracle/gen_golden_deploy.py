@@ -1,4 +1,5 @@
-"""Fixture for the small vendor deploy writers (dipoorlet/deploy/deploy_{atlas,imx,magicmind,snpe,ti}.py):
+"""Fixture for the vendor deploy writers (dipoorlet/deploy/deploy_{atlas,imx,magicmind,snpe,ti,rv,stpu}.py;
+stpu also with --stpu_wg):
 the reference's own calibrate -> save / reduce / load clip values -> to_deploy on the two small seeded
 models, per platform -> tests/golden/<model>/deploy_vendors.json (clip-value file texts in, deploy file
 texts out).
@@ -22,7 +23,7 @@ import torchvision  # noqa: E402,F401
 from oracle import ref_shim  # noqa: E402
 from oracle.gen_golden import GOLD, N_IMG  # noqa: E402
 
-PLATFORMS = ("atlas", "imx", "magicmind", "snpe", "ti")
+PLATFORMS = ("atlas", "imx", "magicmind", "snpe", "ti", "rv", "stpu")   # --stpu_wg crashes in the reference (NodeProto.get_attribute_value)
 
 
 def main():
@@ -37,14 +38,15 @@ def main():
         model = ol.load(os.path.join(d, "model.onnx"))
         images = np.load(os.path.join(d, "images.npy"))
         out = {}
-        for platform in PLATFORMS:
+        for case in PLATFORMS:
+            platform, wg = case.split("+")[0], case.endswith("+wg")
             tmp = tempfile.mkdtemp(prefix="dpl_gold_deploy_")
             W.write_input_dir(images, os.path.join(tmp, "data"), "input")
             g = RU.ONNXGraph(ref_shim.from_lite(model), tmp, platform, None)
             args = types.SimpleNamespace(
                 input_dir=os.path.join(tmp, "data"), output_dir=tmp, data_num=N_IMG, world_size=1, rank=0,
                 local_rank=0, act_quant="minmax", deploy=platform, bins=2048, threshold=0.99999,
-                optim_transformer=False, skip_layers=[], model=None, model_type=None)
+                optim_transformer=False, skip_layers=[], model=None, model_type=None, stpu_wg=wg)
             act, w = RTC.tensor_calibration(g, args)
             RU.save_clip_val(act, w, args, act_fname="act_clip_val.json.rank0", weight_fname="weight_clip_val.json.rank0")
             RU.reduce_clip_val(1, args)
@@ -52,7 +54,7 @@ def main():
             before = set(os.listdir(tmp))
             to_deploy(g, act, w, args)
             written = sorted(set(os.listdir(tmp)) - before)
-            out[platform] = {"act_clip_val": open(os.path.join(tmp, "act_clip_val.json")).read(),
+            out[case] = {"act_clip_val": open(os.path.join(tmp, "act_clip_val.json")).read(),
                              "weight_clip_val": open(os.path.join(tmp, "weight_clip_val.json")).read(),
                              "files": {f: open(os.path.join(tmp, f)).read() for f in written}}
             shutil.rmtree(tmp)

@@ -251,9 +251,9 @@ def test_graph_ir_equals_reference(mname, tmp_path):
 
 
 @pytest.mark.parametrize("mname", MODELS)
-@pytest.mark.parametrize("platform", ["atlas", "imx", "magicmind", "snpe", "ti"])
+@pytest.mark.parametrize("platform", ["atlas", "imx", "magicmind", "snpe", "ti", "rv", "stpu"])
 def test_vendor_deploy_files_byte_identical(mname, platform, tmp_path):
-    """to_deploy for the five small vendor formats: fed the clip-value files the reference wrote, the
+    """to_deploy for the seven vendor formats (rv: four files incl. the YAML anchors of merged records): fed the clip-value files the reference wrote, the
     product reloads them (load_clip_val: scalar vs per-channel weights per platform) and must write the same
     deploy files byte for byte (tests/golden/*/deploy_vendors.json, oracle/gen_golden_deploy.py)."""
     from dipoorlet_b200.cli_args import make_args
@@ -270,3 +270,42 @@ def test_vendor_deploy_files_byte_identical(mname, platform, tmp_path):
     to_deploy(graph, act, weight, args)
     for fname, text in gold["files"].items():
         assert (tmp_path / fname).read_text() == text, fname
+
+
+def test_stpu_winograd_weight_ranges(tmp_path):
+    """`-D stpu --stpu_wg`: the reference crashes here (deploy_stpu.py:72-81 calls NodeProto.get_attribute_value), so
+    there is no fixture; the product's output is checked against the rule itself: every 3x3 stride-1 group-1 Conv
+    gets `layer_<name>: {wg: true}` and the symmetric range of G k G^T over its kernels, everything else is
+    unchanged from the file without the flag."""
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.deploy import to_deploy
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.utils import load_clip_val
+    d, model, images, calib = _load("tiny_r50")
+    gold = json.load(open(os.path.join(d, "deploy_vendors.json")))["stpu"]
+    (tmp_path / "act_clip_val.json").write_text(gold["act_clip_val"])
+    (tmp_path / "weight_clip_val.json").write_text(gold["weight_clip_val"])
+    graph = ONNXGraph(model, str(tmp_path), "stpu")
+    args = make_args(input_dir="unused", data_num=8, deploy="stpu", output_dir=str(tmp_path), stpu_wg=True)
+    act, weight = load_clip_val(args)
+    to_deploy(graph, act, weight, args)
+    got = json.load(open(tmp_path / "stpu_minmax.json"))
+    plain = json.loads(gold["files"]["stpu_minmax.json"])
+    G = np.array([[2, 0, 0], [1, 1, 1], [1, -1, 1], [0, 0, 2]], dtype=np.float32)
+    wg_nodes = [n for n in graph.graph.node if n.op_type == "Conv" and n.attrs.get("group", 1) == 1
+                and list(n.attrs["kernel_shape"]) == [3, 3] and list(n.attrs.get("strides", [1, 1])) == [1, 1]]
+    assert wg_nodes
+    for n in wg_nodes:
+        assert got["layer_" + n.name] == {"wg": True}
+        w = np.asarray(graph.get_initializer(n.input[1]))
+        bound = max(np.abs(G.dot(w[i, j]).dot(G.T)).max() for i in range(w.shape[0]) for j in range(w.shape[1]))
+        assert got[n.name + "_weights"]["max"] == pytest.approx(float(bound), rel=1e-6)
+        assert got[n.name + "_weights"]["min"] == -got[n.name + "_weights"]["max"]
+    touched = {n.name for n in wg_nodes}
+    for k, v in plain.items():
+        owner = k.rsplit("_", 1)[0]
+        if owner in touched and k.endswith(("_weights", "_bias")):
+            continue
+        if isinstance(v, dict) and "emin" in v and any(k in n.output for n in wg_nodes):
+            continue
+        assert got[k] == v, k
