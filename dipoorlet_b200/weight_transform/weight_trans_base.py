@@ -1,23 +1,24 @@
 from .. import dist_helper
 from ..graph import load_graph
 from ..tensor_cali import find_clip_val_minmax_weight, tensor_calibration
-from ..utils import ONNXGraph, logger, update_model_path
+from ..utils import ONNXGraph, load_clip_val, logger, save_clip_val, update_model_path
 from .adaround import adaround
 from .bias_correction import bias_correction
 from .brecq import brecq
+from .update_bn import update_bn
 from .weight_equalization import weight_equalization
 
 
 def weight_calibration(onnx_graph, act_clip_val, weight_clip_val, args):
     """Ordering of the weight transforms (dipoorlet/weight_transform/weight_trans_base.py:15-68):
     bias correction (rank 0, all images) -> weight equalisation (+ re-calibration) -> adaround ->
-    brecq / qdrop. After it the model, args and clip values are identical on every rank.
+    BatchNorm statistics update (+ re-calibration) -> adaround -> brecq / qdrop. After it the model, args and
+    clip values are identical on every rank.
       -> (graph_after_wt, graph_ori, act_clip_val, weight_clip_val)
-    Not on the B200 hot path (no BASELINE.json config uses them): --update_bn,
-    --sparse raise NotImplementedError instead of being silently ignored."""
-    for flag in ("update_bn", "sparse"):
-        if getattr(args, flag, False):
-            raise NotImplementedError(f"--{flag} is outside the B200 hot path (see DESIGN.md, out of scope)")
+    Not built (no BASELINE.json config uses it): --sparse raises NotImplementedError instead
+    of being silently ignored."""
+    if getattr(args, "sparse", False):
+        raise NotImplementedError("--sparse is outside the B200 hot path (see DESIGN.md, out of scope)")
     graph_after_wt = ONNXGraph()
     graph_after_wt.copy_from(onnx_graph)
     if args.bc:
@@ -38,6 +39,22 @@ def weight_calibration(onnx_graph, act_clip_val, weight_clip_val, args):
         graph_after_wt = load_graph(args.model, args.output_dir, onnx_graph.deploy,
                                     onnx_graph.model_type, do_simplify=False)
         act_clip_val, weight_clip_val = tensor_calibration(graph_after_wt, args)   # weight_trans_base.py:36
+    if getattr(args, "update_bn", False):
+        if dist_helper.get_rank() == 0:
+            update_bn(graph_after_wt, act_clip_val, weight_clip_val, args)
+        dist_helper.barrier()
+        update_model_path('update_bn_model', args)
+        graph_after_wt = load_graph(args.model, args.output_dir, onnx_graph.deploy,
+                                    onnx_graph.model_type, do_simplify=False)
+        # weight_trans_base.py:44-49: the reference re-calibrates on rank 0's shard alone and passes the result
+        # through the clip-value files; our calibrators are collective and world-size invariant, so every rank
+        # calls them - the file round trip (float64 activations, per-tensor weights collapsed) is kept.
+        logger.info("Re calibration...")
+        act_clip_val, weight_clip_val = tensor_calibration(graph_after_wt, args)
+        if dist_helper.get_rank() == 0:
+            save_clip_val(act_clip_val, weight_clip_val, args)
+        dist_helper.barrier()
+        act_clip_val, weight_clip_val = load_clip_val(args)
     if args.adaround:
         args.acti_quant = False
         graph_after_wt = adaround(onnx_graph, graph_after_wt, act_clip_val, weight_clip_val, args)

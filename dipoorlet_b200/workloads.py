@@ -210,6 +210,41 @@ def build_mobilenetv2(seed=0, width_mult=1.0, num_classes=1000, image=224):
     return b.finish(x, (num_classes,))
 
 
+def build_preact_net(seed=0, width=8, blocks=2, num_classes=10, image=32):
+    """A small pre-activation residual net whose BatchNormalization nodes follow a Relu or an Add, so that no
+    simplifier can fold them into a Conv: the model family `--update_bn` exists for (update_bn.py:13-25)."""
+    gen = np.random.default_rng(seed)
+
+    def w(*shape):
+        fan_in = int(np.prod(shape[1:]))
+        return (gen.standard_normal(shape) * (2.0 / fan_in) ** .5).astype(np.float32)
+
+    def bn(b, x, c):
+        return b.add("BatchNormalization", [x], {"epsilon": 1e-5, "momentum": 0.9},
+                     [("scale", gen.uniform(0.5, 1.5, c).astype(np.float32)),
+                      ("bias", (gen.standard_normal(c) * 0.1).astype(np.float32)),
+                      ("mean", (gen.standard_normal(c) * 0.2).astype(np.float32)),
+                      ("var", gen.uniform(0.5, 1.5, c).astype(np.float32))])
+
+    def conv(b, x, ci, co, k, stride=1):
+        return b.add("Conv", [x], {"dilations": [1, 1], "group": 1, "kernel_shape": [k, k],
+                                   "pads": [k // 2] * 4, "strides": [stride, stride]},
+                     [("weight", w(co, ci, k, k)), ("bias", (gen.standard_normal(co) * 0.05).astype(np.float32))])
+
+    b = _Builder("preact", (3, image, image))
+    x = b.add("Relu", [conv(b, "input", 3, width, 3)])
+    for _ in range(blocks):
+        y = conv(b, b.add("Relu", [bn(b, x, width)]), width, width, 3)
+        y = conv(b, b.add("Relu", [y]), width, width, 1)
+        x = b.add("Add", [x, y])
+    x = b.add("Relu", [bn(b, x, width)])
+    x = b.add("GlobalAveragePool", [x])
+    x = b.add("Flatten", [x], {"axis": 1})
+    x = b.add("Gemm", [x], {"alpha": 1.0, "beta": 1.0, "transB": 1},
+              [("weight", w(num_classes, width)), ("bias", np.zeros(num_classes, np.float32))])
+    return b.finish(x, (num_classes,))
+
+
 def synthetic_images(n, shape=(3, 224, 224), seed=0, start=0):
     """Image `idx` is a function of (seed, idx) only, so shards and the CPU baseline see
     the same data whatever the batch size. float32 N(0, 1), [n, 1, C, H, W]."""

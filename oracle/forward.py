@@ -82,6 +82,11 @@ def run_node(node, ins, attrs):
         return x
     if op == "Concat":
         return torch.cat(ins, attrs["axis"])
+    if op == "BatchNormalization":
+        # ONNX opset 9-14, inference: (x - mean) / sqrt(var + eps) * scale + B, per channel (axis 1)
+        shape = [1, -1] + [1] * (x.dim() - 2)
+        scale, bias, mean, var = (t.reshape(shape) for t in ins[1:5])
+        return (x - mean) / torch.sqrt(var + attrs.get("epsilon", 1e-5)) * scale + bias
     if op == "QuantizeLinear":
         scale, zp = ins[1], (ins[2] if len(ins) > 2 else torch.zeros((), dtype=torch.uint8))
         lo, hi = (0, 255) if zp.dtype == torch.uint8 else (-128, 127)

@@ -71,3 +71,21 @@ def octav(batch, seg_abssum, seg_nnz, k_const, out_s, out_iters=None, max_iter=2
     unsigned = int(round((1 / 4 ** 8 / 3) / k_const))       # k = 1 / 4**8 / 3 / unsigned (forward_net.py:319-328)
     for k, (b, x) in enumerate(_segs(batch)):
         out_s[k] = float(O.octav_stats({"x": [x]}, unsigned_of=lambda m: unsigned)["x"]["optimal_s"][0])
+
+
+def fakequant(x, scale, zero_point=None, qlo=-128, qhi=127, axis=None, drop_prob=1.0, seed=0, out=None):
+    """K5 stand-in: QuantizeLinear + DequantizeLinear of the ONNX operator spec (round half even, saturate),
+    no QDrop (the host-logic tests never enable it)."""
+    assert drop_prob >= 1.0
+    shape = [1] * x.dim()
+    if scale.numel() > 1:
+        shape[axis] = -1
+    s = scale.reshape(shape)
+    zp = 0.0 if zero_point is None else zero_point.to(torch.float32).reshape(shape)
+    y = (torch.clamp(torch.round(x / s) + zp, qlo, qhi) - zp) * s
+    global _n
+    _n += 1
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y

@@ -229,3 +229,58 @@ def test_mse_on_a_dynamic_sym_platform(monkeypatch, tmp_path):
         assert np.allclose(act[k], ref[k], rtol=2e-6, atol=1e-7), (k, act[k], ref[k])
     # the rule matters: post-ReLU blobs differ from the unsigned = 1 result
     assert any(not np.allclose(ref[k], plain[k], rtol=1e-4) for k in ref)
+
+
+@pytest.mark.parametrize("algo", ["minmax", "hist"])
+def test_weight_calibration_update_bn_like_the_reference(algo, monkeypatch, tmp_path):
+    """weight_calibration(--update_bn) end to end on the CPU stand-ins against the reference's own run
+    (tests/golden/tiny_preact, oracle/gen_golden_update_bn.py): the rewritten running mean / "var" (np.std, as the
+    reference computes it) of all three BatchNormalization nodes, the saved model, and the clip values of the
+    re-calibration after their round trip through the clip-value files."""
+    from dipoorlet_b200 import engine as eng
+    from dipoorlet_b200 import forward_net as fwd
+    from dipoorlet_b200 import onnx_lite as ol
+    from dipoorlet_b200 import workloads as W
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.tensor_cali import tensor_calibration
+    from dipoorlet_b200.weight_transform import weight_calibration
+    monkeypatch.setattr(fwd, "K", fake_kernels)
+    monkeypatch.setattr(eng, "K", fake_kernels)
+    fwd._SESSIONS.clear()
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_preact")
+    model = ol.load(os.path.join(gold_dir, "model.onnx"))
+    images = np.load(os.path.join(gold_dir, "images.npy"))
+    W.write_input_dir(images, str(tmp_path / "data"), "input")
+    graph = ONNXGraph(model, str(tmp_path), "trt")
+    args = make_args(input_dir=str(tmp_path / "data"), data_num=images.shape[0], deploy="trt", act_quant=algo,
+                     output_dir=str(tmp_path), calib_bs=3, _test_device="cpu", update_bn=True)
+    suffix = "" if algo == "minmax" else "_" + algo
+    gold = json.load(open(os.path.join(gold_dir, f"wt_update_bn{suffix}_clip.json")))
+    act, weight = tensor_calibration(graph, args)
+    assert list(act) == list(gold["act_before"])
+    g2, g_ori, act2, weight2 = weight_calibration(graph, act, weight, args)
+    assert g_ori is graph
+    saved = ol.load(os.path.join(str(tmp_path), "update_bn_model.onnx"))
+    stats = np.load(os.path.join(gold_dir, f"wt_update_bn{suffix}.npz"))
+    assert len(stats.files) == 6
+    for name in stats.files:
+        for got in (g2.get_initializer(name), saved.graph.initializers[name]):
+            # clip values that differ in the last bit of the forward (batched here, per image there) move a
+            # handful of roundings by one quantisation step: 5e-5 of a mean at most on this model
+            assert got.dtype == np.float32 and np.allclose(got, stats[name], rtol=2e-4, atol=2e-5), name
+        assert not np.allclose(model.graph.initializers[name], stats[name], rtol=1e-3)
+    # fed the reference's own clip values, the statistics are the reference's to fp32 rounding of the reductions
+    fwd._SESSIONS.clear()
+    from dipoorlet_b200.weight_transform.update_bn import update_bn
+    ref_act = {k: [np.float32(v[0]), np.float32(v[1])] for k, v in gold["act_before"].items()}
+    g3 = update_bn(graph, ref_act, weight, args)
+    for name in stats.files:
+        assert np.allclose(g3.get_initializer(name), stats[name], rtol=3e-6, atol=3e-7), name
+    assert list(act2) == list(gold["act"])
+    for k, v in gold["act"].items():
+        assert isinstance(act2[k][0], np.float64)          # reloaded from act_clip_val.json (utils.py:355-356)
+        assert np.allclose([act2[k][0], act2[k][1]], v, rtol=1e-4, atol=1e-5), (k, act2[k], v)
+    assert list(weight2) == list(gold["weight"])
+    for k, v in gold["weight"].items():
+        assert np.allclose(weight2[k][0], v[0], rtol=2e-4, atol=2e-5) and np.allclose(weight2[k][1], v[1], rtol=2e-4, atol=2e-5), k
