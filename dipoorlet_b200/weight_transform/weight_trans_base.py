@@ -5,6 +5,7 @@ from ..utils import ONNXGraph, load_clip_val, logger, save_clip_val, update_mode
 from .adaround import adaround
 from .bias_correction import bias_correction
 from .brecq import brecq
+from .sparse_quant import sparse_quant
 from .update_bn import update_bn
 from .weight_equalization import weight_equalization
 
@@ -12,13 +13,10 @@ from .weight_equalization import weight_equalization
 def weight_calibration(onnx_graph, act_clip_val, weight_clip_val, args):
     """Ordering of the weight transforms (dipoorlet/weight_transform/weight_trans_base.py:15-68):
     bias correction (rank 0, all images) -> weight equalisation (+ re-calibration) -> adaround ->
-    BatchNorm statistics update (+ re-calibration) -> adaround -> brecq / qdrop. After it the model, args and
-    clip values are identical on every rank.
-      -> (graph_after_wt, graph_ori, act_clip_val, weight_clip_val)
-    Not built (no BASELINE.json config uses it): --sparse raises NotImplementedError instead
-    of being silently ignored."""
-    if getattr(args, "sparse", False):
-        raise NotImplementedError("--sparse is outside the B200 hot path (see DESIGN.md, out of scope)")
+    BatchNorm statistics update (+ re-calibration) -> adaround -> brecq / qdrop, or, with --sparse, the
+    prune-and-quantise finetune INSTEAD of those two. After it the model, args and clip values are identical on
+    every rank.
+      -> (graph_after_wt, graph_ori, act_clip_val, weight_clip_val)"""
     graph_after_wt = ONNXGraph()
     graph_after_wt.copy_from(onnx_graph)
     if args.bc:
@@ -55,6 +53,9 @@ def weight_calibration(onnx_graph, act_clip_val, weight_clip_val, args):
             save_clip_val(act_clip_val, weight_clip_val, args)
         dist_helper.barrier()
         act_clip_val, weight_clip_val = load_clip_val(args)
+    if getattr(args, "sparse", False):
+        graph_after_wt = sparse_quant(onnx_graph, graph_after_wt, act_clip_val, weight_clip_val, args)
+        return graph_after_wt, onnx_graph, act_clip_val, weight_clip_val
     if args.adaround:
         args.acti_quant = False
         graph_after_wt = adaround(onnx_graph, graph_after_wt, act_clip_val, weight_clip_val, args)

@@ -284,3 +284,59 @@ def test_weight_calibration_update_bn_like_the_reference(algo, monkeypatch, tmp_
     assert list(weight2) == list(gold["weight"])
     for k, v in gold["weight"].items():
         assert np.allclose(weight2[k][0], v[0], rtol=2e-4, atol=2e-5) and np.allclose(weight2[k][1], v[1], rtol=2e-4, atol=2e-5), k
+
+
+@pytest.mark.parametrize("mname,tag", [("tiny_r50", "unstruction"), ("tiny_r50", "nv24"), ("tiny_r50", "unstruction_30"),
+                                       ("tiny_mbv2", "nv24")])
+def test_weight_calibration_sparse_like_the_reference(mname, tag, monkeypatch, tmp_path):
+    """weight_calibration(--sparse) on the CPU stand-ins against the weights the REFERENCE deployed for the same
+    model, images and hyper-parameters (tests/golden/*/wt_sparse_*.npz, oracle/gen_golden_sparse.py).
+    Always: every deployed weight sits on its channel's quantisation grid and the sparsity pattern holds exactly.
+    Parity: the finetune moves weights by several quantisation steps, so a last-bit difference in a layer's input
+    can grow into different roundings there and downstream (one fixture, unstruction_30 on tiny_r50, does:
+    94 % identical); the others come out bit-identical here. Bar: >= 90 % identical weights, the first five layers
+    bit-identical."""
+    from dipoorlet_b200 import engine as eng
+    from dipoorlet_b200 import forward_net as fwd
+    from dipoorlet_b200 import onnx_lite as ol
+    from dipoorlet_b200 import workloads as W
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.tensor_cali import tensor_calibration
+    from dipoorlet_b200.weight_transform import weight_calibration
+    monkeypatch.setattr(fwd, "K", fake_kernels)
+    monkeypatch.setattr(eng, "K", fake_kernels)
+    fwd._SESSIONS.clear()
+    pattern, rate = tag.split("_")[0], (0.3 if tag.endswith("_30") else 0.5)
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", mname)
+    model = ol.load(os.path.join(gold_dir, "model.onnx"))
+    images = np.load(os.path.join(gold_dir, "images.npy"))
+    W.write_input_dir(images, str(tmp_path / "data"), "input")
+    graph = ONNXGraph(model, str(tmp_path), "trt")
+    args = make_args(input_dir=str(tmp_path / "data"), data_num=images.shape[0], deploy="trt", act_quant="minmax",
+                     output_dir=str(tmp_path), calib_bs=8, _test_device="cpu", sparse=True, sparse_rate=rate,
+                     pattern=pattern, ada_bs=4, ada_epoch=12, adaround=True)      # --sparse wins over --adaround
+    act, weight = tensor_calibration(graph, args)
+    g2, g_ori, act2, weight2 = weight_calibration(graph, act, weight, args)
+    assert g_ori is graph and act2 is act and weight2 is weight
+    assert os.path.exists(os.path.join(str(tmp_path), "sparse_quant.onnx"))
+    assert not os.path.exists(os.path.join(str(tmp_path), "adaround.onnx"))
+    gold = np.load(os.path.join(gold_dir, f"wt_sparse_{tag}.npz"))
+    learnable = [n.input[1] for n in graph.graph.node if n.op_type in ("Conv", "Gemm")]
+    assert sorted(gold.files) == sorted(learnable)
+    total = same = 0
+    for i, name in enumerate(learnable):
+        got, want = g2.get_initializer(name), gold[name]
+        step = (np.maximum(np.abs(weight[name][0]), np.abs(weight[name][1])) / 127).astype(np.float32)
+        q = got / np.where(step == 0, 1, step).reshape([-1] + [1] * (got.ndim - 1))
+        assert np.allclose(q, np.round(q), atol=1e-3) and np.abs(q).max() <= 127 + 1e-3, name
+        if pattern == "nv24":
+            groups = (np.transpose(got, (0, 2, 3, 1)) if got.ndim == 4 else got).reshape(-1, 4)
+            assert ((groups == 0).sum(axis=1) >= 2).all(), name
+        else:
+            assert (got == 0).sum() >= int(rate * got.size), name
+        eq = np.abs(got - want) <= 1e-7
+        if i < 5:
+            assert eq.all(), (name, int((~eq).sum()))
+        total, same = total + eq.size, same + int(eq.sum())
+    assert same / total >= 0.90, same / total
