@@ -32,6 +32,7 @@ _c_int = ctypes.c_int
 _c_size = ctypes.c_size_t
 _c_dbl = ctypes.c_double
 _c_flt = ctypes.c_float
+_c_u32 = ctypes.c_uint32
 
 # name -> (restype, argtypes); must list every symbol of include/dpl_b200.h
 SIGNATURES = {
@@ -59,6 +60,9 @@ SIGNATURES = {
     "dpl_adaround_step_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_u64, _c_flt, _c_flt, _c_flt,
                                        _c_flt, _c_flt, _c_flt, _c_flt, _c_flt, _c_int, _c_flt,
                                        _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "dpl_adaround_step_peer_f32": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_u32, _c_vp, _c_vp, _c_int, _c_u64,
+                                            _c_flt, _c_flt, _c_flt, _c_flt, _c_flt, _c_flt, _c_flt, _c_flt,
+                                            _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "dpl_recon_act_f32": (_c_int, [_c_vp, _c_vp, _c_u64, _c_int, _c_int, _c_flt, _c_flt, _c_flt, _c_flt,
                                    _c_u64, _c_vp, _c_vp]),
     "dpl_recon_act_bwd_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_u64, _c_int, _c_int, _c_flt, _c_flt,

@@ -366,6 +366,127 @@ adaround_step_kernel(const float* __restrict__ grad_w, const float* __restrict__
   }
 }
 
+// ---- K6 step with the gradient all-reduce inside (opt-in, DPL_PEER_ALLREDUCE=1) ----
+// The reference averages dL/dW over ranks with DistributedDataParallel's bucketed NCCL all-reduce before
+// Adam runs (adaround.py:121, brecq.py:163). Here every rank keeps its dL/dW in a buffer that all peers have
+// mapped over NVLink (CUDA IPC through torch's symmetric memory) and the step kernel itself reads the W
+// copies, adds them in rank order — so every replica computes bit-identical sums and stays identical — and
+// applies the update: one launch and W reads of the gradient instead of an all-reduce (2 (W - 1) / W
+// transfers plus a launch-latency-bound collective) followed by the step.
+// Arrival protocol, per layer: each rank owns W 32-bit words, word r = the last epoch at which rank r
+// announced "my gradient slot for this epoch is written". Every CTA stores its own rank's word on all peers
+// (release, system scope; the same value from every CTA, so the store is idempotent and no CTA depends on
+// another one being scheduled) and waits (acquire, bounded) until its own words show this epoch for all
+// peers. Epochs only grow, so no reset and no second barrier is needed; the gradient lives in two slots
+// used alternately: a rank can only overwrite slot e % 2 in iteration e + 2, after the arrival of iteration
+// e + 1, by which time every peer has finished the step kernel of iteration e that read it.
+constexpr int kMaxPeers = 8;
+struct PeerCfg {
+  const float* grads[kMaxPeers];   // this epoch's gradient slot on every rank (rank order; [rank] is local)
+  uint32_t* words[kMaxPeers];      // the arrival words of every rank
+  int world, rank;
+  uint32_t epoch;                  // >= 1, identical on all ranks, +1 per iteration
+};
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// peer memory: coherent at system scope, never through the non-coherent path
+__device__ __forceinline__ float4 ld_sys4(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_sys1(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256, 4)
+adaround_step_peer_kernel(const PeerCfg pc, const float* __restrict__ wfloor, const float* __restrict__ scale,
+                          int n_channels, uint64_t inner, uint64_t n, StepCfg c, float* __restrict__ alpha,
+                          float* __restrict__ m, float* __restrict__ v, double* __restrict__ reg_out,
+                          const float* __restrict__ sched, int vec, int* __restrict__ error_flag) {
+  int late = 0;
+  if (threadIdx.x < pc.world) {
+    __threadfence_system();
+    st_release_sys_u32(pc.words[threadIdx.x] + pc.rank, pc.epoch);
+    const uint32_t* mine = pc.words[pc.rank] + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys_u32(mine) - pc.epoch) < 0) {
+      if (clock64() - t0 > 4000000000ll) {   // ~2 s: a peer is gone; report instead of hanging the GPU
+        late = 1;
+        break;
+      }
+    }
+  }
+  if (__syncthreads_or(late)) {              // leave alpha / m / v untouched
+    if (threadIdx.x == 0 && error_flag) atomicExch(error_flag, 1);
+    return;
+  }
+  if (sched) {
+    c.beta = sched[0];
+    c.bc1 = sched[1];
+    c.bc2_sqrt = sched[2];
+  }
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool small = n < (1ull << 32);
+  double reg_acc = 0.0;
+  if (vec) {
+    const uint64_t n4 = n >> 2;
+    const float4* f4 = reinterpret_cast<const float4*>(wfloor);
+    float4* a4 = reinterpret_cast<float4*>(alpha);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    for (uint64_t i = tid; i < n4; i += stride) {
+      float4 g = ld_sys4(reinterpret_cast<const float4*>(pc.grads[0]) + i);
+      for (int r = 1; r < pc.world; ++r) {
+        const float4 t = ld_sys4(reinterpret_cast<const float4*>(pc.grads[r]) + i);
+        g.x += t.x;
+        g.y += t.y;
+        g.z += t.z;
+        g.w += t.w;
+      }
+      const float4 f = ldg_stream4(f4 + i);
+      float4 a = a4[i], mm = m4[i], vv = v4[i];
+      const float s = scale[n_channels == 1 ? 0 : channel_of(i << 2, inner, n_channels, small)];
+      float reg = step1(g.x, f.x, s, c, a.x, mm.x, vv.x);
+      reg += step1(g.y, f.y, s, c, a.y, mm.y, vv.y);
+      reg += step1(g.z, f.z, s, c, a.z, mm.z, vv.z);
+      reg += step1(g.w, f.w, s, c, a.w, mm.w, vv.w);
+      a4[i] = a;
+      m4[i] = mm;
+      v4[i] = vv;
+      reg_acc += (double)reg;
+    }
+  } else {
+    for (uint64_t i = tid; i < n; i += stride) {
+      float g = ld_sys1(pc.grads[0] + i);
+      for (int r = 1; r < pc.world; ++r) g += ld_sys1(pc.grads[r] + i);
+      const float s = scale[n_channels == 1 ? 0 : channel_of(i, inner, n_channels, small)];
+      float a = alpha[i], mi = m[i], vi = v[i];
+      reg_acc += (double)step1(g, wfloor[i], s, c, a, mi, vi);
+      alpha[i] = a;
+      m[i] = mi;
+      v[i] = vi;
+    }
+  }
+  if (reg_out) {
+    reg_acc = warp_sum(reg_acc);
+    if ((threadIdx.x & 31) == 0 && reg_acc != 0.0) atomicAdd(reg_out, reg_acc);
+  }
+}
+
 inline bool al16q(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 inline unsigned ew_grid(uint64_t n, int per_thread) {
@@ -471,5 +592,43 @@ extern "C" int dpl_adaround_step_f32(const float* d_grad_w, const float* d_wfloo
   adaround_step_kernel<<<stream_grid(vec ? n / 4 : n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_grad_w, d_wfloor, d_scale, n_channels, inner, n, c, d_alpha, d_m, d_v, d_reg, d_sched, vec);
   DPL_LAUNCH_CHECK("adaround_step_kernel");
+  return 0;
+}
+
+extern "C" int dpl_adaround_step_peer_f32(const void* const* peer_grads, void* const* peer_words, int world,
+                                          int rank, uint32_t epoch, const float* d_wfloor,
+                                          const float* d_scale, int n_channels, uint64_t inner, float qmin,
+                                          float qmax, float beta, float reg_alpha, float lr, float b1, float b2,
+                                          float eps, int step, float* d_alpha, float* d_m, float* d_v,
+                                          double* d_reg, const float* d_sched, int* d_error, void* stream) {
+  DPL_REQUIRE(peer_grads && peer_words && d_wfloor && d_scale && d_alpha && d_m && d_v, "null pointer");
+  DPL_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "bad world / rank");
+  DPL_REQUIRE(n_channels >= 1 && inner >= 1 && step >= 1 && epoch >= 1, "bad arguments");
+  const uint64_t n = (uint64_t)n_channels * inner;
+  PeerCfg pc;
+  int vec = al16q(d_wfloor) && al16q(d_alpha) && al16q(d_m) && al16q(d_v) && (inner & 3u) == 0;
+  for (int r = 0; r < kMaxPeers; ++r) {
+    pc.grads[r] = r < world ? static_cast<const float*>(peer_grads[r]) : nullptr;
+    pc.words[r] = r < world ? static_cast<uint32_t*>(peer_words[r]) : nullptr;
+    if (r < world) {
+      DPL_REQUIRE(pc.grads[r] && pc.words[r], "null peer pointer");
+      vec = vec && al16q(pc.grads[r]);
+    }
+  }
+  pc.world = world;
+  pc.rank = rank;
+  pc.epoch = epoch;
+  const double bc1 = 1.0 - pow((double)b1, (double)step);
+  const double bc2 = 1.0 - pow((double)b2, (double)step);
+  // the mean over ranks (DistributedDataParallel) is folded into the step
+  StepCfg c = {qmin, qmax, beta, reg_alpha, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), 1.0f / (float)world};
+  // at most 2 CTAs per SM: every CTA announces to every peer, and all of them can be resident at once
+  uint64_t g = ((vec ? n / 4 : n) + 255) / 256;
+  const uint64_t cap = (uint64_t)sm_count() * 2;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  adaround_step_peer_kernel<<<(unsigned)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      pc, d_wfloor, d_scale, n_channels, inner, n, c, d_alpha, d_m, d_v, d_reg, d_sched, vec, d_error);
+  DPL_LAUNCH_CHECK("adaround_step_peer_kernel");
   return 0;
 }

@@ -246,6 +246,25 @@ def adaround_step(grad_w, wfloor, scale, qmin, qmax, beta, alpha, m, v, step, re
     _count()
 
 
+def adaround_step_peer(peer_grads, peer_words, rank, epoch, wfloor, scale, qmin, qmax, beta, alpha, m, v, step,
+                       reg_alpha=0.01, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, reg_out=None, sched=None, error=None):
+    """K6 step with the all-reduce of dL/dW inside. peer_grads / peer_words: lists of
+    `world` device addresses (ints) in rank order; see dpl_adaround_step_peer_f32."""
+    world = len(peer_grads)
+    assert len(peer_words) == world and 0 <= rank < world
+    c = scale.numel()
+    inner = wfloor.numel() // c
+    grads = (ctypes.c_void_p * world)(*[int(p) for p in peer_grads])
+    words = (ctypes.c_void_p * world)(*[int(p) for p in peer_words])
+    check(lib().dpl_adaround_step_peer_f32(grads, words, world, int(rank), int(epoch), wfloor.data_ptr(),
+                                           scale.data_ptr(), c, inner, float(qmin), float(qmax), float(beta),
+                                           float(reg_alpha), float(lr), float(b1), float(b2), float(eps),
+                                           int(step), alpha.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                           _lib._ptr(reg_out), _lib._ptr(sched), _lib._ptr(error), _stream()),
+          "dpl_adaround_step_peer_f32")
+    _count()
+
+
 def recon_act(o, relu, quant=None, prob=1.0, seed=0, out=None, seed_dev=None):
     """K6 epilogue forward. quant: None or (scale, qmin, qmax) per-tensor."""
     y = torch.empty_like(o) if out is None else out

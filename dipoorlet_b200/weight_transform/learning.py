@@ -15,6 +15,72 @@ from .. import kernels as K
 from ..utils import logger
 
 
+_PEER_POOL = {}   # device index -> (symmetric float32 buffer, its rendezvous handle)
+
+
+class PeerGradients:
+    """dL/dW of every layer of the block in a buffer that all ranks have mapped over NVLink (torch symmetric
+    memory = CUDA IPC), so that the step kernel can read the world's gradients itself instead of waiting for
+    an NCCL all-reduce (K.adaround_step_peer). Per layer: two gradient slots used alternately
+    and `world` arrival words. One buffer per process, grown when a block needs more, so that the IPC
+    rendezvous is paid a few times per run and not per layer.
+    Opt-in: DPL_PEER_ALLREDUCE=1, world > 1 on one NVLink domain."""
+
+    WORDS = 64     # floats reserved in front of a layer's slots for its arrival words (world <= 8 used)
+
+    def __init__(self, layers, dev):
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank = dist_helper.get_world_size(), dist_helper.get_rank()
+        if self.world > 8:
+            raise RuntimeError("DPL_PEER_ALLREDUCE supports at most 8 ranks (one NVLink domain)")
+        self.epoch = 0
+        self.error = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.layout, need = [], 0
+        for layer in layers:
+            n = layer.round_mask.numel()
+            slot = (n + 3) & ~3                                   # keep both slots 16-byte aligned
+            self.layout.append((need, n, slot))                   # words at `need`, slots behind them
+            need += self.WORDS + 2 * slot
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        pooled = _PEER_POOL.get(key)
+        if pooled is None or pooled[0].numel() < need:
+            # every rank sees the same layers, so every rank grows at the same call (symmetric allocation)
+            buf = symm.empty(max(need + need // 2, 1 << 20), dtype=torch.float32, device=dev)
+            pooled = (buf, symm.rendezvous(buf, torch.distributed.group.WORLD))
+            _PEER_POOL[key] = pooled
+        self.buf, self.hdl = pooled
+        # the previous block's last step kernels may still be reading this buffer on a slower rank and writing
+        # their arrival into ours: all ranks drain first, then the words are cleared, then everybody starts
+        torch.cuda.synchronize(dev)
+        self.hdl.barrier()
+        for off, _, _ in self.layout:
+            self.buf[off:off + self.WORDS].zero_()
+        torch.cuda.synchronize(dev)
+        self.hdl.barrier()
+
+    def next_epoch(self):
+        self.epoch += 1
+
+    def slot(self, li):
+        """This rank's gradient slot of layer `li` for the current epoch (flat float32 view)."""
+        off, n, slot = self.layout[li]
+        start = off + self.WORDS + (self.epoch & 1) * slot
+        return self.buf[start:start + n]
+
+    def pointers(self, li):
+        """-> (gradient slot of the current epoch, arrival words) on every rank, as device addresses."""
+        off, _, slot = self.layout[li]
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        inside = self.buf.data_ptr() - ptrs[self.rank]     # the tensor's offset in the (symmetric) allocation
+        base = [p + inside for p in ptrs]
+        g = (off + self.WORDS + (self.epoch & 1) * slot) * 4
+        return [b + g for b in base], [b + off * 4 for b in base]
+
+    def check(self):
+        if int(self.error.item()):
+            raise RuntimeError("peer all-reduce: a rank did not arrive within the kernel's time limit")
+
+
 def _seed(base, it, layer):
     return (base * 1000003 + it * 131 + layer * 7 + 12345) & (2 ** 63 - 1)
 
@@ -45,7 +111,7 @@ def learning_round_mask(layers, q_in, tgt, reg, batch_size, max_epoch, fp_in=Non
             os.environ["DPL_TCGEN05"] = saved[2]
 
 
-def _iteration(layers, x, t, reg_alpha, world, loss_acc, sched, seeds):
+def _iteration(layers, x, t, reg_alpha, world, loss_acc, sched, seeds, peer=None):
     """One optimisation step on the mini-batch (x, t). Every per-iteration scalar (beta, Adam bias
     corrections, mask seeds) is read from device memory (`sched`, `seeds`, filled by the
     schedule kernel), so the same launch sequence serves every iteration — eagerly or as a
@@ -68,10 +134,17 @@ def _iteration(layers, x, t, reg_alpha, world, loss_acc, sched, seeds):
     for li in range(last, -1, -1):
         layer = layers[li]
         gx, gw = layer.dense_backward(acts[li], layer.w_soft, go, need_dx=li > 0)
-        if world > 1:
-            torch.distributed.all_reduce(gw)   # SUM; the 1/world is folded into the step
-        K.adaround_step(gw, layer.wfloor, layer.scale, layer.q_min, layer.q_max, 0.0, layer.round_mask,
-                        layer.m, layer.v, 1, reg_alpha=reg_alpha, grad_scale=1.0 / world, sched=sched)
+        if peer is not None:               # the step kernel reads every rank's dL/dW over NVLink itself
+            peer.slot(li).copy_(gw.reshape(-1))
+            grads, words = peer.pointers(li)
+            K.adaround_step_peer(grads, words, peer.rank, peer.epoch, layer.wfloor, layer.scale, layer.q_min,
+                                 layer.q_max, 0.0, layer.round_mask, layer.m, layer.v, 1, reg_alpha=reg_alpha,
+                                 sched=sched, error=peer.error)
+        else:
+            if world > 1:
+                torch.distributed.all_reduce(gw)   # SUM; the 1/world is folded into the step
+            K.adaround_step(gw, layer.wfloor, layer.scale, layer.q_min, layer.q_max, 0.0, layer.round_mask,
+                            layer.m, layer.v, 1, reg_alpha=reg_alpha, grad_scale=1.0 / world, sched=sched)
         if li > 0:
             go = K.recon_act_bwd(outs[li - 1], gx, **cfgs[li - 1])
 
@@ -89,6 +162,10 @@ def _learn(layers, q_in, tgt, reg, batch_size, max_epoch, fp_in, drop, log_every
     t_max = float(reg.temp_anneal.t_max)
     ratio = 0.5 if drop else 1.0
     x_all = q_in if ratio >= 1.0 else torch.empty_like(q_in)
+
+    peer = None
+    if world > 1 and os.environ.get("DPL_PEER_ALLREDUCE", "0") == "1":
+        peer = PeerGradients(layers, dev)
 
     def schedule():
         K.recon_schedule(d_iter, sched, seeds, t_max, seed_base=seed)
@@ -144,11 +221,15 @@ def _learn(layers, q_in, tgt, reg, batch_size, max_epoch, fp_in, drop, log_every
                 graph.replay()
             else:
                 schedule()
-                _iteration(layers, x_all[st:ed], tgt[st:ed], reg.alpha, world, loss_acc, sched, seeds)
+                if peer is not None:
+                    peer.next_epoch()
+                _iteration(layers, x_all[st:ed], tgt[st:ed], reg.alpha, world, loss_acc, sched, seeds, peer)
         if epoch % log_every == 0 and rank0:
             logger.info("Epoch: {:<5} L2 Loss: {:>10.3f} Beta: {:>3.3f}".format(
                 epoch, float(loss_acc.item()), float(sched[0].item())))
     loss = float(loss_acc.item()) if max_epoch > 0 else float("nan")
+    if peer is not None:
+        peer.check()
     reg.beta = float(sched[0].item()) if max_epoch > 0 else reg.beta
     if rank0:
         for layer in layers:

@@ -168,6 +168,21 @@ int dpl_adaround_step_f32(const float* d_grad_w, const float* d_wfloor, const fl
                           float grad_scale, float* d_alpha, float* d_m, float* d_v,
                           double* d_reg, const float* d_sched, void* stream);
 
+/* K6 step with the gradient all-reduce inside: replaces DistributedDataParallel's NCCL
+ * all-reduce of dL/dW (adaround.py:121, brecq.py:163) followed by the step. peer_grads / peer_words are HOST
+ * arrays of `world` (<= 8) device pointers, in rank order, into buffers every rank has mapped (CUDA IPC, e.g.
+ * torch symmetric memory): peer_grads[r] = rank r's dL/dW slot for this epoch, peer_words[r] = rank r's
+ * `world` 32-bit arrival words (zeroed once, before the first call, with a barrier after the zeroing).
+ * The kernel announces this rank's arrival at `epoch` (>= 1, +1 per call on every rank, the slot
+ * alternating between two buffers), waits for every peer's (bounded: sets *d_error and leaves the state
+ * untouched after ~2 s), sums the `world` gradients in rank order (bit-identical on every rank), scales by
+ * 1 / world and applies dpl_adaround_step_f32's update. */
+int dpl_adaround_step_peer_f32(const void* const* peer_grads, void* const* peer_words, int world, int rank,
+                               uint32_t epoch, const float* d_wfloor, const float* d_scale, int n_channels,
+                               uint64_t inner, float qmin, float qmax, float beta, float reg_alpha, float lr,
+                               float b1, float b2, float eps, int step, float* d_alpha, float* d_m,
+                               float* d_v, double* d_reg, const float* d_sched, int* d_error, void* stream);
+
 /* K6 epilogues — layer activation of the reconstruction loop: y = [drop-]fakequant(relu(o))
  * (AdaQLayer.forward tail, weight_transform/ada_quant_layer.py:245-251; quant_acti :28-36),
  * its backward (round() has zero gradient: only non-quantised elements pass), the fused

@@ -92,7 +92,7 @@ def test_ctypes_signatures_match_the_header(dpl_built):
         if t in (ctypes.c_void_p, ctypes.c_char_p) or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
             return "ptr"
         return {ctypes.c_int: "i32", ctypes.c_float: "f32", ctypes.c_double: "f64", ctypes.c_size_t: "size",
-                ctypes.c_uint64: "i64", ctypes.c_longlong: "i64"}[t]
+                ctypes.c_uint64: "i64", ctypes.c_longlong: "i64", ctypes.c_uint32: "i32"}[t]
 
     protos = _prototypes()
     assert set(protos) == set(_lib.SIGNATURES)
