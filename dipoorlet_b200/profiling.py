@@ -5,6 +5,7 @@ The reference rebuilds two ONNXRuntime sessions PER IMAGE (forward_net.py:467-48
 reduces on the host; here both graphs run batched on the GPU, every cosine is three sums
 from one K7b launch per tensor per batch, and ranks are combined with one all-reduce."""
 import heapq
+import os
 import math
 
 import numpy as np
@@ -77,6 +78,13 @@ def quantize_profiling_multipass(graph_after_wt, graph_ori, act_clip_val, weight
                 c = _cosines(a, b)
                 out_sum[i] += c.sum()
                 out_min[i] = torch.minimum(out_min[i], c.min())
+            if getattr(args, "savefp", False) and dist_helper.get_rank() == 0:
+                # --savefp (profiling.py:82-86): rank 0's fp network outputs, one raw float32 file per image
+                save_path = os.path.join(args.output_dir, 'output', t)
+                os.makedirs(save_path, exist_ok=True)
+                host = a.detach().cpu().numpy().astype(np.float32)
+                for j in range(host.shape[0]):
+                    host[j].tofile(os.path.join(save_path, 'onnx-output-{}.bin'.format(b0 + j)))
         del fp, q
     n_local = torch.tensor([float(ed - st)], dtype=torch.float64, device=dev)
     if dist_helper.is_dist():

@@ -89,3 +89,13 @@ def fakequant(x, scale, zero_point=None, qlo=-128, qhi=127, axis=None, drop_prob
         out.copy_(y)
         return out
     return y
+
+
+def cosine3(a, b, out):
+    """K7b stand-in: per segment (first axis) sum(a b), sum(a a), sum(b b) in float64, accumulated into out."""
+    x, y = a.reshape(a.shape[0], -1).double(), b.reshape(b.shape[0], -1).double()
+    out[:, 0] += (x * y).sum(1)
+    out[:, 1] += (x * x).sum(1)
+    out[:, 2] += (y * y).sum(1)
+    global _n
+    _n += 1

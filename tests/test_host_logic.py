@@ -340,3 +340,50 @@ def test_weight_calibration_sparse_like_the_reference(mname, tag, monkeypatch, t
             assert eq.all(), (name, int((~eq).sum()))
         total, same = total + eq.size, same + int(eq.sum())
     assert same / total >= 0.90, same / total
+
+
+@pytest.mark.parametrize("mname", ["tiny_r50", "tiny_mbv2"])
+def test_profiling_cosines_and_savefp_like_the_reference(mname, monkeypatch, tmp_path):
+    """quantize_profiling_multipass on the CPU stand-ins: the bias-corrected model the reference profiled
+    (weights from tests/golden/*/wt_bc.npz) must give the reference's layer / output cosines
+    (profiling_bc.json, profiling.py:34-99), and --savefp must write rank 0's fp network outputs as
+    output/<tensor>/onnx-output-<i>.bin, raw float32, one file per image (profiling.py:82-86)."""
+    from dipoorlet_b200 import engine as eng
+    from dipoorlet_b200 import forward_net as fwd
+    from dipoorlet_b200 import onnx_lite as ol
+    from dipoorlet_b200 import profiling as prof
+    from dipoorlet_b200 import workloads as W
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.tensor_cali import find_clip_val_minmax_weight
+    from oracle import forward as OF
+    for mod in (fwd, eng, prof):
+        monkeypatch.setattr(mod, "K", fake_kernels)
+    fwd._SESSIONS.clear()
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", mname)
+    model = ol.load(os.path.join(gold_dir, "model.onnx"))
+    images = np.load(os.path.join(gold_dir, "images.npy"))
+    calib = json.load(open(os.path.join(gold_dir, "calibration.json")))
+    act = {k: [np.float64(v[0]), np.float64(v[1])] for k, v in calib["minmax"]["act"].items()}
+    W.write_input_dir(images, str(tmp_path / "data"), "input")
+    graph = ONNXGraph(model, str(tmp_path), "trt")
+    args = make_args(input_dir=str(tmp_path / "data"), data_num=images.shape[0], deploy="trt", act_quant="minmax",
+                     output_dir=str(tmp_path), calib_bs=3, _test_device="cpu", savefp=True)
+    g2 = ONNXGraph()
+    g2.copy_from(graph)
+    bc = np.load(os.path.join(gold_dir, "wt_bc.npz"))
+    for k in bc.files:
+        g2.set_initializer(k, bc[k])
+    layer, model_cos, qlist = prof.quantize_profiling_multipass(g2, graph, act, find_clip_val_minmax_weight(g2, args), args)
+    gold = json.load(open(os.path.join(gold_dir, "profiling_bc.json")))
+    assert list(layer) == list(gold["layer"])
+    for k, v in gold["layer"].items():
+        assert abs(float(layer[k]) - v) < 1e-5, (k, layer[k], v)
+    for k, v in gold["model"].items():
+        assert abs(float(model_cos[k][0]) - v[0]) < 1e-5 and abs(float(model_cos[k][1]) - v[1]) < 1e-5
+    assert os.path.exists(os.path.join(str(tmp_path), "quant_model.onnx"))
+    out_name = graph.network_outputs[0]
+    for i in range(images.shape[0]):
+        got = np.fromfile(os.path.join(str(tmp_path), "output", out_name, f"onnx-output-{i}.bin"), dtype=np.float32)
+        want = OF.forward_all(model, {"input": images[i]})[out_name].reshape(-1)
+        assert got.shape == want.shape and np.allclose(got, want, rtol=1e-5, atol=1e-6)
