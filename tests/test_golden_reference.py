@@ -309,3 +309,29 @@ def test_stpu_winograd_weight_ranges(tmp_path):
         if isinstance(v, dict) and "emin" in v and any(k in n.output for n in wg_nodes):
             continue
         assert got[k] == v, k
+
+
+@pytest.mark.parametrize("mname", MODELS)
+def test_quant_graph_with_skip_layers_equals_reference(mname, tmp_path):
+    """--skip_layers (quantize.py:29-31): the named layers get no Q/DQ on their weight or inputs and are not in the
+    quantised-node list; the rewritten graph is the reference's node for node
+    (tests/golden/*/quant_graph_skip_layers.json, oracle/gen_golden_skip_layers.py)."""
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.quantize import quant_graph
+    d, model, images, calib = _load(mname)
+    want = json.load(open(os.path.join(d, "quant_graph_skip_layers.json")))
+    full = json.load(open(os.path.join(d, "quant_graph_platforms.json")))["trt"]
+    graph = ONNXGraph(model, str(tmp_path), "trt")
+    args = make_args(input_dir="unused", data_num=8, deploy="trt", output_dir=str(tmp_path),
+                     skip_layers=want["skip_layers"])
+    gold_w = np.load(os.path.join(d, "weight_clip.npz"))
+    clip = {k: [np.float64(v[0]), np.float64(v[1])] for k, v in calib["minmax"]["act"].items()}
+    for key in gold_w.files:
+        name, i = key.rsplit("|", 1)
+        clip.setdefault(name, [None, None])[int(i)] = gold_w[key]
+    gq, qlist = quant_graph(graph, copy.deepcopy(clip), args)
+    assert [n.name for n in qlist] == want["quant_node_list"]
+    assert not set(want["skip_layers"]) & set(want["quant_node_list"])
+    assert [[n.op_type, n.name, list(n.input), list(n.output)] for n in gq.graph.node] == want["nodes"]
+    assert len(want["nodes"]) < len(full["nodes"])          # the fixture does exercise the flag
