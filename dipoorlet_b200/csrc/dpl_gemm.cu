@@ -1328,6 +1328,206 @@ conv1x1_px_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
   }
 }
 
+// ---- tap-table convolution with the activations through TMEM (experimental, DPL_TAPS_TS=1) -----------
+// conv_taps_tf32x3_kernel's problem (shifted windows of the channel-last padded copy, one accumulating GEMM
+// step per tap and 32-channel block) on conv1x1_px_tf32x3_kernel's machinery: the X tile [128 q][32 ci] lands
+// in shared memory (K-major, 128-byte swizzle — the layout the existing tensor map produces), four transform
+// warps read their own row of it (thread <-> padded pixel; the swizzle spreads the 32 rows of a warp over all
+// banks: 4 wavefronts per 16-byte access, the minimum), split it into the TF32 pattern and its residual and
+// tcgen05.st both into TMEM; the MMAs take A from TMEM and only the weight tiles from shared memory.
+// Per 32-channel block and tap, shared-memory traffic drops from 176 KB (both operands in shared memory,
+// X_lo written back) to 16 (X landing) + 16 (W, W_lo landing) + 16 (transform read) + 24 (MMA reads of W) KB.
+// 128 q x 64 co tiles, 256 TMEM columns, 96 KB of shared memory: two CTAs per SM, one tile's epilogue
+// overlaps the other's main loop. One leading accumulator (no hi_alt): NOT YET RUN ON HARDWARE.
+__global__ void __launch_bounds__(kPxThreads, 2)
+conv_taps_ts_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                           const __grid_constant__ CUtensorMap tmWlo, const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full[kPxStages], s_empty[kPxStages], s_aready[2], s_aempty[2], s_acc_full;
+  __shared__ uint32_t s_tmem_base;
+  __shared__ int s_fail;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tiles = (smem_addr(smem_raw) + 1023u) & ~1023u;
+  const uint8_t* tiles_ptr = smem_raw + (tiles - smem_addr(smem_raw));
+  const int co0 = blockIdx.x * kPxBN;                      // output-channel groups fastest: X tiles shared in L2
+  const long long q0 = (long long)blockIdx.y * kBM;
+  const int num_kb = (p.c_in + kBK - 1) / kBK;
+  const int total_iters = p.n_taps * num_kb;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPxStages; ++s) {
+      bar_init(smem_addr(&s_full[s]), 1);
+      bar_init(smem_addr(&s_empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      bar_init(smem_addr(&s_aready[a]), 4);   // one arrival per transform warp
+      bar_init(smem_addr(&s_aempty[a]), 1);
+    }
+    bar_init(smem_addr(&s_acc_full), 1);
+    s_fail = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_addr(&s_tmem_base)),
+                 "r"(kPxTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem_base;
+  const uint32_t acc_hi = tmem + 128u, acc_lo = tmem + 192u;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer: X tile (shifted rows of the padded copy), W and W_lo tiles of this tap =====
+    for (int it = 0; it < total_iters; ++it) {
+      const int s = it % kPxStages;
+      const uint32_t ph = (it / kPxStages) & 1;
+      if (!bar_wait(smem_addr(&s_empty[s]), ph ^ 1)) {
+        s_fail = 1;
+        break;
+      }
+      const uint32_t full = smem_addr(&s_full[s]);
+      bar_expect_tx(full, kPxStageBytes);
+      const int kb = it / p.n_taps, tap = it - kb * p.n_taps;
+      const int k0 = kb * kBK;
+      const uint32_t x_tile = tiles + s * kPxStageBytes, w_tile = x_tile + kPxXBytes, wlo_tile = w_tile + kPxWBytes;
+      tma_load_3d(x_tile, &tmX, k0, (int)q0 + p.tap_shift[tap], 0, full);
+      tma_load_3d(w_tile, &tmW, k0, co0, tap, full);
+      tma_load_3d(wlo_tile, &tmWlo, k0, co0, tap, full);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer: A from TMEM, three MMAs per K step =====
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kPxBN >> 3) << 17) |
+                           ((uint32_t)(kBM >> 4) << 24);      // f32 accumulate, tf32 x tf32, both K-major
+    bool failed = false;
+    for (int it = 0; it < total_iters; ++it) {
+      const int s = it % kPxStages, a = it & 1;
+      if (!bar_wait(smem_addr(&s_aready[a]), (it >> 1) & 1)) {
+        s_fail = 1;
+        failed = true;
+        break;
+      }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t w_tile = tiles + s * kPxStageBytes + kPxXBytes, wlo_tile = w_tile + kPxWBytes;
+      const uint32_t a_hi = tmem + (uint32_t)(a * 64), a_lo = a_hi + 32u;
+#pragma unroll
+      for (int j = 0; j < kBK / kUmmaK; ++j) {
+        const uint64_t db = desc_k_major(w_tile, j), dbl = desc_k_major(wlo_tile, j);
+        const uint32_t accumulate = (it > 0 || j > 0) ? 1u : 0u;
+        mma_tf32_ts(acc_lo, a_lo + (uint32_t)(j * kUmmaK), db, idesc, accumulate);
+        mma_tf32_ts(acc_lo, a_hi + (uint32_t)(j * kUmmaK), dbl, idesc, 1u);
+        mma_tf32_ts(acc_hi, a_hi + (uint32_t)(j * kUmmaK), db, idesc, accumulate);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_addr(&s_empty[s]))
+                   : "memory");
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_addr(&s_aempty[a]))
+                   : "memory");
+    }
+    if (!failed)
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_addr(&s_acc_full))
+                   : "memory");
+  } else if (warp >= 4) {
+    // ===== transform warps: own row of the X tile -> {TF32 pattern, residual} -> TMEM; then the epilogue =====
+    const int quarter = warp - 4;                 // TMEM lane quarter this warp may access (warp % 4)
+    const int m = quarter * 32 + lane;            // padded pixel of this thread within the tile
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    bool ok = true;
+    for (int it = 0; it < total_iters && ok; ++it) {
+      const int s = it % kPxStages, a = it & 1;
+      ok = bar_wait(smem_addr(&s_full[s]), (it / kPxStages) & 1) &&
+           bar_wait(smem_addr(&s_aempty[a]), ((it >> 1) & 1) ^ 1);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) break;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // row m of a 128-byte-swizzled tile: logical 16-byte chunk c sits at chunk c ^ (m & 7)
+      const uint8_t* row = tiles_ptr + s * kPxStageBytes + m * 128;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(row + ((c ^ (m & 7)) << 4));
+        hi[4 * c + 0] = __float_as_uint(v.x);
+        hi[4 * c + 1] = __float_as_uint(v.y);
+        hi[4 * c + 2] = __float_as_uint(v.z);
+        hi[4 * c + 3] = __float_as_uint(v.w);
+        lo[4 * c + 0] = __float_as_uint(tf32_residual(v.x));
+        lo[4 * c + 1] = __float_as_uint(tf32_residual(v.y));
+        lo[4 * c + 2] = __float_as_uint(tf32_residual(v.z));
+        lo[4 * c + 3] = __float_as_uint(tf32_residual(v.w));
+      }
+      tmem_st32(lane_base + (uint32_t)(a * 64), hi);
+      tmem_st32(lane_base + (uint32_t)(a * 64 + 32), lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&s_aready[a])) : "memory");
+    }
+    if (!ok) s_fail = 1;
+    // ----- epilogue: TMEM lane = padded pixel q, columns = output channels -----
+    if (ok) {
+      ok = bar_wait(smem_addr(&s_acc_full), 0);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) s_fail = 1;
+    }
+    if (ok) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const long long q = q0 + m;
+      bool valid = q < p.q_total;
+      long long out_base = 0;
+      if (valid) {
+        const int img = (int)(q / p.plane);
+        const int r = (int)(q - (long long)img * p.plane);
+        const int hp = r / p.Wp, wp = r - hp * p.Wp;
+        const int ho = hp - p.origin, wo = wp - p.origin;
+        valid = ho >= 0 && ho < p.H && wo >= 0 && wo < p.W;
+        out_base = (((long long)img * p.c_out) * p.H + ho) * p.W + wo;
+      }
+      const long long ch_stride = (long long)p.H * p.W;
+      float rlo = INFINITY, rhi = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < kPxBN / 32; ++c) {
+        uint32_t r[32], r2[32];
+        tmem_ld32(lane_base + 128u + (uint32_t)(c * 32), r);
+        tmem_ld32(lane_base + 192u + (uint32_t)(c * 32), r2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (valid) {
+          const int cb = co0 + c * 32;
+          float* dst = p.Y + out_base + (long long)cb * ch_stride;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (cb + j < p.c_out) {
+              float v = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+              if (p.bias) v += __ldg(p.bias + cb + j);
+              if (p.relu) v = fmaxf(v, 0.f);
+              dst[(long long)j * ch_stride] = v;
+              if (p.Y2) p.Y2[(dst - p.Y) + (long long)j * ch_stride] = relu_keep_nan(v);
+              rlo = fminf(rlo, v);
+              rhi = fmaxf(rhi, v);
+            }
+          }
+        }
+      }
+      warp_range_flush(rlo, rhi, p.bmin, p.bmax, p.rmin, p.rmax);
+    }
+  }
+  __syncwarp();
+  if (s_fail) {
+    if ((threadIdx.x & 31) == 0 && p.error_flag) atomicExch(p.error_flag, 1);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kPxTmemCols) : "memory");
+  }
+}
+
 // Unswizzled 3-D fp32 map (px, ci, img) with a [128 x 32 x 1] box for the pixel-major kernel.
 int make_map_px(CUtensorMap* map, const float* base, uint64_t hw, uint64_t c_in, uint64_t n_img);
 
@@ -1704,7 +1904,12 @@ extern "C" int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, con
   CUtensorMap tmX, tmW, tmWlo;
   int st = make_map(&tmX, d_xp, (uint64_t)c_in, (uint64_t)total_rows, 1, (uint64_t)c_in, 0, kBM, false);
   if (st) return st;
-  const int bn = c_out <= 64 ? 64 : 128;
+  // experimental variant with the activations through TMEM (conv_taps_ts_tf32x3_kernel): opt-in
+  static const bool taps_ts = [] {
+    const char* e = getenv("DPL_TAPS_TS");
+    return e && e[0] == '1';
+  }();
+  const int bn = taps_ts ? kPxBN : (c_out <= 64 ? 64 : 128);
   st = make_map(&tmW, d_w_taps, (uint64_t)c_in, (uint64_t)c_out, (uint64_t)n_taps, (uint64_t)c_in,
                 (uint64_t)c_out * c_in, (uint32_t)bn, false);
   if (!st)
@@ -1734,6 +1939,23 @@ extern "C" int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, con
   p.bmax = d_blob_max;
   p.rmin = d_relu_min;
   p.rmax = d_relu_max;
+  if (taps_ts) {
+    DPL_REQUIRE((q_total + kBM - 1) / kBM <= 65535, "grid limit (DPL_TAPS_TS)");
+    dim3 grid_ts((unsigned)((c_out + kPxBN - 1) / kPxBN), (unsigned)((q_total + kBM - 1) / kBM), 1);
+    const size_t smem_ts = (size_t)kPxStages * kPxStageBytes + 1024;
+    static bool attr_ts_done = false;
+    if (!attr_ts_done) {
+      int e = cuda_status(cudaFuncSetAttribute(conv_taps_ts_tf32x3_kernel,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts),
+                          "cudaFuncSetAttribute(conv_taps_ts_tf32x3_kernel)");
+      if (e) return e;
+      attr_ts_done = true;
+    }
+    conv_taps_ts_tf32x3_kernel<<<grid_ts, kPxThreads, smem_ts, static_cast<cudaStream_t>(stream)>>>(tmX, tmW, tmWlo,
+                                                                                                   p);
+    DPL_LAUNCH_CHECK("conv_taps_ts_tf32x3_kernel");
+    return 0;
+  }
   dim3 grid((unsigned)((q_total + kBM - 1) / kBM), (unsigned)((c_out + bn - 1) / bn), 1);
   const size_t smem = (size_t)kStages3 * kStageBytes3 + 1024;
   static bool attr_done = false;
