@@ -387,3 +387,37 @@ def test_profiling_cosines_and_savefp_like_the_reference(mname, monkeypatch, tmp
         got = np.fromfile(os.path.join(str(tmp_path), "output", out_name, f"onnx-output-{i}.bin"), dtype=np.float32)
         want = OF.forward_all(model, {"input": images[i]})[out_name].reshape(-1)
         assert got.shape == want.shape and np.allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+def test_reference_import_paths_resolve_to_this_package():
+    """the plugin objects must be reachable at the reference's module paths. In a subprocess (the
+    alias must not leak into the other tests, some of which import the real reference as `dipoorlet`)."""
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+from dipoorlet_b200 import compat
+compat.install(); compat.install()
+from dipoorlet.tensor_cali.basic_algorithm import tensor_cali_dispatcher
+from dipoorlet.tensor_cali import tensor_calibration, find_clip_val_minmax_weight
+from dipoorlet.weight_transform import weight_calibration
+from dipoorlet.deploy import to_deploy
+from dipoorlet.deploy.deploy_default import deploy_dispatcher
+from dipoorlet.utils import ONNXGraph, logger, dispatch_functool, save_clip_val, load_clip_val, reduce_clip_val
+from dipoorlet.forward_net import ActivationCache, forward_get_minmax, forward_get_hist, forward_net_octav
+from dipoorlet.quantize import quant_graph
+from dipoorlet.platform_settings import platform_setting_table
+import dipoorlet.forward_net as a, dipoorlet_b200.forward_net as b
+import dipoorlet_b200.tensor_cali.basic_algorithm as B
+import dipoorlet_b200.deploy.deploy_default as D
+assert a is b and tensor_cali_dispatcher is B.tensor_cali_dispatcher and deploy_dispatcher is D.deploy_dispatcher
+@tensor_cali_dispatcher.register("third_party")
+def third_party(graph, args, **kw):
+    return {"blob": [0.0, 1.0]}
+assert B.tensor_cali_dispatcher("third_party", None, None) == {"blob": [0.0, 1.0]}
+assert B.tensor_cali_dispatcher("no_such_algo", None, None) is None          # default fn: logs, returns None
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
