@@ -19,11 +19,12 @@ from .weight_transform import weight_calibration
 
 def main(argv=None):
     args = build_parser().parse_args(argv)
-    if args.slurm or args.mpirun:
-        sys.exit("--slurm / --mpirun cluster bootstraps are out of scope: launch with torchrun")
     if args.optim_transformer or args.model_type is not None or args.quant_format == "QOP":
         sys.exit("transformer / QOperator paths are outside the B200 hot path (CNN QDQ calibration only)")
-    rank, local_rank, world = dist_helper.init_from_env()
+    if args.slurm or args.mpirun:
+        rank, local_rank, world = dist_helper.init_from_launcher("slurm" if args.slurm else "mpirun")
+    else:
+        rank, local_rank, world = dist_helper.init_from_env()
     if args.output_dir is None:
         args.output_dir = os.path.join(os.path.abspath(os.path.dirname(args.model)), 'results')
     if rank == 0:

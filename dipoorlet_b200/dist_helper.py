@@ -9,10 +9,12 @@ reference at world_size = 1 over the same images. Payloads are 
 (<= 2 MB), so each phase is a single latency-bound collective.
 
 The helpers accept CPU tensors too (gloo), which is how tests/ cover the N > 1 path
-without GPUs. Cluster launchers (slurm / mpirun parsing, dipoorlet/dist_helper.py:8-49)
-are out of scope: torchrun's environment variables are the only bootstrap.
+without GPUs. The cluster launchers of the reference (dipoorlet/dist_helper.py:8-49) are reduced to what
+they are — translations of the launcher's environment into torchrun's variables (`env_from_slurm`,
+`env_from_mpi`), after which `init_from_env` is the only bootstrap.
 """
 import os
+import re
 
 import torch
 import torch.distributed as dist
@@ -20,6 +22,40 @@ import torch.distributed as dist
 
 def is_dist():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def env_from_mpi(environ):
+    """`--mpirun` (dist_helper.py:8-23): Open MPI's rank / size, the master from the HNP URI unless given."""
+    out = {"RANK": environ["OMPI_COMM_WORLD_RANK"], "WORLD_SIZE": environ["OMPI_COMM_WORLD_SIZE"],
+           "MASTER_PORT": environ.get("MASTER_PORT", "29500")}
+    if "MASTER_ADDR" in environ:
+        out["MASTER_ADDR"] = environ["MASTER_ADDR"]
+    else:
+        out["MASTER_ADDR"] = re.search(r'.*tcp://((\d{1,3}\.){3}\d{1,3})[:,].*',
+                                       environ["OMPI_MCA_orte_hnp_uri"]).group(1)
+    return out
+
+
+def env_from_slurm(environ):
+    """`--slurm` (dist_helper.py:26-49): rank / size from SLURM, port from the job id, master = the first node of
+    SLURM_NODELIST, whose name encodes its address after an 8-character prefix ("SH-IDC1-10-5-30-[12,14]" ->
+    10.5.30.12) — the reference's cluster convention, kept as is."""
+    nodes = environ["SLURM_NODELIST"]
+    if "[" in nodes:
+        beg = nodes.find("[")
+        ends = [p for p in (nodes.find("-", beg), nodes.find(",", beg)) if p >= 0]
+        nodes = nodes[:min(ends + [1000])].replace("[", "")
+    return {"RANK": str(int(environ["SLURM_PROCID"])), "WORLD_SIZE": str(int(environ["SLURM_NTASKS"])),
+            "MASTER_PORT": str(24553 + int(environ["SLURM_JOB_ID"]) % 10000),
+            "MASTER_ADDR": nodes[8:].replace("-", ".")}
+
+
+def init_from_launcher(kind):
+    """kind: 'slurm' | 'mpirun'. Ranks map to GPUs round robin (rank % device_count), as in the reference."""
+    os.environ.update((env_from_slurm if kind == "slurm" else env_from_mpi)(os.environ))
+    n_dev = max(torch.cuda.device_count(), 1) if torch.cuda.is_available() else 1
+    os.environ["LOCAL_RANK"] = str(int(os.environ["RANK"]) % n_dev)
+    return init_from_env()
 
 
 def init_from_env(backend=None):

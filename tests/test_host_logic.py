@@ -421,3 +421,14 @@ print("ok")
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_launcher_environment_translation_equals_reference():
+    """--slurm / --mpirun: what the reference's init_from_slurm / init_from_mpi export before they call
+    init_process_group (dist_helper.py:8-49; tests/golden/launcher_env.json, oracle/gen_golden_launcher_env.py)."""
+    from dipoorlet_b200 import dist_helper as d
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "launcher_env.json")))
+    for case in gold["slurm"]:
+        assert d.env_from_slurm(case["env"]) == case["exports"], case
+    for case in gold["mpi"]:
+        assert d.env_from_mpi(case["env"]) == case["exports"], case
