@@ -18,6 +18,24 @@ from ..utils import logger
 _PEER_POOL = {}   # device index -> (symmetric float32 buffer, its rendezvous handle)
 
 
+def peer_layout(sizes, words=64):
+    """Float offsets of the per-layer regions of the peer buffer: [(words_offset, n, slot)], total floats.
+    A region is `words` arrival words followed by two gradient slots of `slot` = n rounded up to 4 floats, so
+    that every slot starts on a 16-byte boundary (the step kernel reads float4)."""
+    layout, need = [], 0
+    for n in sizes:
+        slot = (int(n) + 3) & ~3
+        layout.append((need, int(n), slot))
+        need += words + 2 * slot
+    return layout, need
+
+
+def peer_offsets(layout, li, epoch, words=64):
+    """-> (float offset of layer li's gradient slot for `epoch`, float offset of its arrival words)."""
+    off, _, slot = layout[li]
+    return off + words + (epoch & 1) * slot, off
+
+
 class PeerGradients:
     """dL/dW of every layer of the block in a buffer that all ranks have mapped over NVLink (torch symmetric
     memory = CUDA IPC), so that the step kernel can read the world's gradients itself instead of waiting for
@@ -35,12 +53,7 @@ class PeerGradients:
             raise RuntimeError("DPL_PEER_ALLREDUCE supports at most 8 ranks (one NVLink domain)")
         self.epoch = 0
         self.error = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.layout, need = [], 0
-        for layer in layers:
-            n = layer.round_mask.numel()
-            slot = (n + 3) & ~3                                   # keep both slots 16-byte aligned
-            self.layout.append((need, n, slot))                   # words at `need`, slots behind them
-            need += self.WORDS + 2 * slot
+        self.layout, need = peer_layout([layer.round_mask.numel() for layer in layers], self.WORDS)
         key = dev.index if dev.index is not None else torch.cuda.current_device()
         pooled = _PEER_POOL.get(key)
         if pooled is None or pooled[0].numel() < need:
@@ -63,18 +76,15 @@ class PeerGradients:
 
     def slot(self, li):
         """This rank's gradient slot of layer `li` for the current epoch (flat float32 view)."""
-        off, n, slot = self.layout[li]
-        start = off + self.WORDS + (self.epoch & 1) * slot
-        return self.buf[start:start + n]
+        start, _ = peer_offsets(self.layout, li, self.epoch, self.WORDS)
+        return self.buf[start:start + self.layout[li][1]]
 
     def pointers(self, li):
         """-> (gradient slot of the current epoch, arrival words) on every rank, as device addresses."""
-        off, _, slot = self.layout[li]
+        g, w = peer_offsets(self.layout, li, self.epoch, self.WORDS)
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         inside = self.buf.data_ptr() - ptrs[self.rank]     # the tensor's offset in the (symmetric) allocation
-        base = [p + inside for p in ptrs]
-        g = (off + self.WORDS + (self.epoch & 1) * slot) * 4
-        return [b + g for b in base], [b + off * 4 for b in base]
+        return [p + inside + g * 4 for p in ptrs], [p + inside + w * 4 for p in ptrs]
 
     def check(self):
         if int(self.error.item()):

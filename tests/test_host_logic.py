@@ -432,3 +432,19 @@ def test_launcher_environment_translation_equals_reference():
         assert d.env_from_slurm(case["env"]) == case["exports"], case
     for case in gold["mpi"]:
         assert d.env_from_mpi(case["env"]) == case["exports"], case
+
+
+def test_peer_gradient_buffer_layout():
+    """learning.peer_layout / peer_offsets (the opt-in peer all-reduce): regions do not overlap,
+    every slot is 16-byte aligned, the two slots of a layer alternate with the epoch and never touch its words."""
+    from dipoorlet_b200.weight_transform.learning import peer_layout, peer_offsets
+    sizes = [64 * 64 * 9, 1000 * 3 + 1, 7, 2048 * 512]
+    layout, need = peer_layout(sizes)
+    spans = []
+    for li, n in enumerate(sizes):
+        g0, w = peer_offsets(layout, li, 2)
+        g1, w1 = peer_offsets(layout, li, 3)
+        assert w == w1 and g0 % 4 == 0 and g1 % 4 == 0 and w % 4 == 0
+        assert g0 == w + 64 and g1 >= g0 + n and peer_offsets(layout, li, 4)[0] == g0
+        spans.append((w, g1 + n))
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] <= need
