@@ -448,3 +448,50 @@ def test_peer_gradient_buffer_layout():
         assert g0 == w + 64 and g1 >= g0 + n and peer_offsets(layout, li, 4)[0] == g0
         spans.append((w, g1 + n))
     assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] <= need
+
+
+def test_two_input_model_calibrates_in_reference_order(monkeypatch, tmp_path):
+    """A model with two network inputs: every input is read from {input_dir}/{input_name}/{idx}.bin
+    (forward_net.py:459-464) and the clip-value dict lists the network inputs first, then the node outputs in
+    node order (forward_net.py:195-198, 220-227). Values == the oracle statistics on the engine's blobs."""
+    import torch
+    from dipoorlet_b200 import forward_net as fwd
+    from dipoorlet_b200 import onnx_lite as ol
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.engine import Engine
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.tensor_cali import tensor_calibration
+    from oracle import stats as O
+    monkeypatch.setattr(fwd, "K", fake_kernels)
+    fwd._SESSIONS.clear()
+    rng = np.random.default_rng(4)
+    g = ol.Graph("two_inputs")
+    g.inputs += [ol.ValueInfo("left", ol.FLOAT, [1, 3, 16, 16]), ol.ValueInfo("right", ol.FLOAT, [1, 2, 16, 16])]
+    for name, shape in (("wl", (4, 3, 3, 3)), ("wr", (4, 2, 1, 1)), ("fc_w", (5, 4)), ("fc_b", (5,))):
+        g.initializers[name] = (rng.standard_normal(shape) * 0.3).astype(np.float32)
+    conv = {"dilations": [1, 1], "group": 1, "strides": [1, 1]}
+    g.nodes += [ol.Node("Conv", ["left", "wl"], ["a"], "Conv_0", dict(conv, kernel_shape=[3, 3], pads=[1, 1, 1, 1])),
+                ol.Node("Conv", ["right", "wr"], ["b"], "Conv_1", dict(conv, kernel_shape=[1, 1], pads=[0, 0, 0, 0])),
+                ol.Node("Add", ["a", "b"], ["s"], "Add_2"), ol.Node("Relu", ["s"], ["r"], "Relu_3"),
+                ol.Node("GlobalAveragePool", ["r"], ["p"], "GlobalAveragePool_4"),
+                ol.Node("Flatten", ["p"], ["f"], "Flatten_5", {"axis": 1}),
+                ol.Node("Gemm", ["f", "fc_w", "fc_b"], ["out"], "Gemm_6", {"alpha": 1.0, "beta": 1.0, "transB": 1})]
+    g.outputs.append(ol.ValueInfo("out", ol.FLOAT, [1, 5]))
+    graph = ONNXGraph(ol.Model(g, ir_version=7, opsets={"": 13}), str(tmp_path), "trt")
+    n = 5
+    feeds = {"left": rng.standard_normal((n, 3, 16, 16)).astype(np.float32),
+             "right": rng.standard_normal((n, 2, 16, 16)).astype(np.float32)}
+    for name, arr in feeds.items():
+        os.makedirs(tmp_path / "data" / name)
+        for i in range(n):
+            arr[i].tofile(str(tmp_path / "data" / name / f"{i}.bin"))
+    args = make_args(input_dir=str(tmp_path / "data"), data_num=n, deploy="trt", output_dir=str(tmp_path),
+                     calib_bs=2, _test_device="cpu", act_quant="hist")
+    act, _ = tensor_calibration(graph, args)
+    assert list(act) == ["left", "right", "a", "b", "s", "r", "p", "f", "out"]
+    blobs = Engine(graph, "cpu", _unit_test_cpu=True).run({k: torch.from_numpy(v) for k, v in feeds.items()}, want="all")
+    blobs = {k: [v[i].numpy() for i in range(n)] for k, v in blobs.items()}
+    mm = O.minmax_stats(blobs)
+    ref = O.clip_hist(mm, O.hist_stats(blobs, mm, 2048), 2048, args.threshold)
+    for k in ref:
+        assert np.allclose(act[k], ref[k], rtol=2e-6, atol=1e-7), (k, act[k], ref[k])
