@@ -335,3 +335,57 @@ def test_quant_graph_with_skip_layers_equals_reference(mname, tmp_path):
     assert not set(want["skip_layers"]) & set(want["quant_node_list"])
     assert [[n.op_type, n.name, list(n.input), list(n.output)] for n in gq.graph.node] == want["nodes"]
     assert len(want["nodes"]) < len(full["nodes"])          # the fixture does exercise the flag
+
+
+@pytest.mark.parametrize("mname", MODELS)
+@pytest.mark.parametrize("platform", ["trt", "snpe"])
+def test_report_lines_equal_reference(mname, platform, tmp_path):
+    """The user-visible report — show_model_profiling_res, show_model_ranges, weight_need_perchannel
+    (profiling.py:199-260) — line for line what the reference logs for the same numbers
+    (tests/golden/*/reports.json, oracle/gen_golden_reports.py): per-layer cosines, the ten worst layers,
+    output cosines, every range with its shape, and on a per-tensor platform the per-layer degradation ranking."""
+    import logging
+    from dipoorlet_b200 import profiling as prof
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.quantize import quant_graph
+    from dipoorlet_b200.utils import logger
+    d, model, images, calib = _load(mname)
+    gold = json.load(open(os.path.join(d, "reports.json")))[platform]
+    pb = json.load(open(os.path.join(d, "profiling_bc.json")))
+    graph = ONNXGraph(model, str(tmp_path), platform)
+    args = make_args(input_dir="unused", data_num=8, deploy=platform, output_dir=str(tmp_path))
+    gold_w = np.load(os.path.join(d, "weight_clip.npz"))
+    act = {k: [np.float64(v[0]), np.float64(v[1])] for k, v in calib["minmax"]["act"].items()}
+    weight = {}
+    for key in gold_w.files:
+        name, i = key.rsplit("|", 1)
+        weight.setdefault(name, [None, None])[int(i)] = gold_w[key]
+    if platform == "snpe":
+        weight = {k: [np.min(v[0]), np.max(v[1])] for k, v in weight.items()}
+    clip = dict(act)
+    clip.update(weight)
+    _, qlist = quant_graph(graph, copy.deepcopy(clip), args)
+    layer = {t: gold["layer"][t] for n in qlist for t in n.output}
+    model_cos = {k: list(v) for k, v in pb["model"].items()}
+
+    class Lines(logging.Handler):
+        def __init__(self):
+            super().__init__()
+            self.lines = []
+
+        def emit(self, record):
+            self.lines.append(record.getMessage())
+
+    h = Lines()
+    logger.addHandler(h)
+    old = logger.level
+    logger.setLevel(logging.INFO)
+    try:
+        prof.show_model_profiling_res(graph, layer, model_cos, qlist, args)
+        prof.show_model_ranges(graph, act, weight, args)
+        prof.weight_need_perchannel(graph, args)
+    finally:
+        logger.removeHandler(h)
+        logger.setLevel(old)
+    assert h.lines == gold["lines"]
