@@ -100,6 +100,16 @@ SIGNATURES = {
     "dpl_maxpool2d_f32": (_c_int, [_c_vp, _c_vp, _c_u64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                    _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp]),
     "dpl_global_avgpool_f32": (_c_int, [_c_vp, _c_vp, _c_u64, _c_u64, _c_vp, _c_vp, _c_vp]),
+    "dpl_tap_conv_tf32": (_c_int, [_c_vp, ctypes.c_longlong, _c_vp, _c_int, _c_vp, _c_int, _c_int, _c_int, _c_int,
+                                   _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp,
+                                   _c_vp, _c_vp, _c_vp]),
+    "dpl_tap_wgrad_tf32": (_c_int, [_c_vp, ctypes.c_longlong, _c_vp, ctypes.c_longlong, _c_vp, _c_int, _c_int,
+                                    _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "dpl_taps_layout_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp]),
+    "dpl_dwconv2d_wgrad_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                        _c_int, _c_int, _c_vp]),
+    "dpl_dwconv2d_dgrad_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                        _c_int, _c_int, _c_vp]),
 }
 
 

@@ -723,3 +723,180 @@ def conv_im2col_forward_x3(x, prepared, kernel, stride, pad, bias=None, out=None
 
 def conv3x3_forward_x3(x, taps, taps_lo, bias=None, relu=False, out=None, scratch=None):
     return conv_taps_forward_x3(x, taps, taps_lo, 3, 1, bias, relu, out, scratch)
+
+
+# ---- K6 dense contraction for k x k / strided / depthwise convolutions (single-pass TF32) -------------------
+def _err_flag(dev):
+    flag = _gemm_err.get(dev)
+    if flag is None:
+        flag = _gemm_err[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return flag
+
+
+def _unsupported(st, what):
+    if st == 10003:
+        raise GemmUnsupported(lib().dpl_last_error().decode("utf-8", "replace"))
+    check(st, what)
+
+
+def _ints(values):
+    return (ctypes.c_int * len(values))(*[int(v) for v in values])
+
+
+class ReconConvPlan(ConvPlan):
+    """Geometry of one learnable convolution on the tap-table kernels: the forward / weight-gradient taps
+    (ConvPlan) plus the data-gradient taps per output-parity class.
+    Supported: 3x3 pad 1 stride 1 / 2, 1x1 pad 0 stride 1 / 2 (dilation 1, no groups)."""
+
+    def __init__(self, n, h, w, ksize, stride, pad):
+        if (ksize, pad) not in ((3, 1), (1, 0)) or stride not in (1, 2):
+            raise GemmUnsupported("recon conv plan: kernel %d stride %d pad %d" % (ksize, stride, pad))
+        ConvPlan.__init__(self, n, h, w, ksize, stride)
+        self.ksize, self.pad = ksize, pad
+        self.q_total = n * self.hp * self.wp
+        # dX[s j + a] = sum over kh with (a + pad - kh) % s == 0 of dY[j + (a + pad - kh) / s] W[kh]: in the
+        # staging copy of dY (same origin / pitch as the forward's q index) that is a row shift of dh * Wp + dw
+        self.dgrad = []
+        for a in range(stride):
+            for b in range(stride):
+                shifts, taps = [], []
+                for kh in range(ksize):
+                    if (a + pad - kh) % stride:
+                        continue
+                    for kw in range(ksize):
+                        if (b + pad - kw) % stride:
+                            continue
+                        dh, dw = (a + pad - kh) // stride, (b + pad - kw) // stride
+                        shifts.append(dh * self.wp + dw)
+                        taps.append(kh * ksize + kw)
+                self.dgrad.append((a, b, shifts, taps))
+        self.c_taps = _ints(range(len(self.shifts)))
+
+
+def taps_layout(w, forward=True, dgrad=False, out_f=None, out_d=None):
+    """w [co][ci][kh][kw] -> (wf [T][co][ci] or None, wd [T][ci][co] or None), see dpl_taps_layout_f32."""
+    _need(w, torch.float32, "w")
+    co, ci = w.shape[0], w.shape[1]
+    t = w[0, 0].numel()
+    wf = (torch.empty((t, co, ci), dtype=torch.float32, device=w.device) if out_f is None else out_f) \
+        if forward else None
+    wd = (torch.empty((t, ci, co), dtype=torch.float32, device=w.device) if out_d is None else out_d) \
+        if dgrad else None
+    check(lib().dpl_taps_layout_f32(w.data_ptr(), _lib._ptr(wf), _lib._ptr(wd), co, ci, t, _stream()),
+          "dpl_taps_layout_f32")
+    _count()
+    return wf, wd
+
+
+def recon_stage_input(x, plan, out=None):
+    """Channel-last zero-bordered staging copy Xp [planes * n * Hp * Wp][ci] of the layer input."""
+    n, ci, hh, ww = x.shape
+    need = plan.total_rows * ci
+    xp = torch.empty(need, dtype=torch.float32, device=x.device) if out is None or out.numel() < need else out
+    check(lib().dpl_pad_plane_f32(x.data_ptr(), xp.data_ptr(), n, ci, hh, ww, plan.stride, plan.origin, plan.hp,
+                                  plan.wp, plan.planes, _stream()), "dpl_pad_plane_f32")
+    _count()
+    return xp
+
+
+def recon_stage_grad(go, plan, out=None):
+    """Staging copy Gp [n * Hp * Wp][co] of the output gradient in the forward's q indexing (zero border)."""
+    n, co, ho, wo = go.shape
+    need = plan.q_total * co
+    gp = torch.empty(need, dtype=torch.float32, device=go.device) if out is None or out.numel() < need else out
+    check(lib().dpl_pad_plane_f32(go.data_ptr(), gp.data_ptr(), n, co, ho, wo, 1, plan.origin, plan.hp, plan.wp, 1,
+                                  _stream()), "dpl_pad_plane_f32")
+    _count()
+    return gp
+
+
+def recon_conv_forward(xp, plan, wf, bias=None, out=None):
+    """Y = conv(X, W) from the staging copy xp and the tap-major filter wf [T][co][ci] (TF32, fp32 accumulate)."""
+    t, co, ci = wf.shape
+    y = torch.empty((plan.n, co, plan.ho, plan.wo), dtype=torch.float32, device=xp.device) if out is None else out
+    st = lib().dpl_tap_conv_tf32(xp.data_ptr(), plan.total_rows, wf.data_ptr(), t, y.data_ptr(), plan.n, ci, co,
+                                 plan.ho, plan.wo, plan.hp, plan.wp, plan.origin, 1, 0, 0, len(plan.shifts),
+                                 plan.c_shifts, plan.c_taps, _lib._ptr(bias), _err_flag(xp.device).data_ptr(),
+                                 _stream())
+    _unsupported(st, "dpl_tap_conv_tf32")
+    _count()
+    return y
+
+
+def recon_conv_wgrad(gp, xp, plan, co, ci, out=None):
+    """dW [co][ci][k][k] from the staging copies of dY (gp) and of the layer input (xp)."""
+    k = plan.ksize
+    dw = torch.empty((co, ci, k, k), dtype=torch.float32, device=gp.device) if out is None else out
+    st = lib().dpl_tap_wgrad_tf32(gp.data_ptr(), plan.q_total, xp.data_ptr(), plan.total_rows, dw.data_ptr(), co, ci,
+                                  k * k, len(plan.shifts), plan.c_shifts, plan.c_taps,
+                                  _err_flag(gp.device).data_ptr(), _stream())
+    _unsupported(st, "dpl_tap_wgrad_tf32")
+    _count()
+    return dw
+
+
+def recon_conv_dgrad(gp, plan, wd, out=None):
+    """dX [n][ci][H][W] from the staging copy of dY and the filter in data-gradient layout wd [T][ci][co];
+    one launch per output-parity class of a strided convolution."""
+    t, ci, co = wd.shape
+    dx = torch.empty((plan.n, ci, plan.h, plan.w), dtype=torch.float32, device=gp.device) if out is None else out
+    if any(not taps for _, _, _, taps in plan.dgrad):
+        dx.zero_()                      # classes no tap reaches (1x1 stride 2)
+    for a, b, shifts, taps in plan.dgrad:
+        if not taps:
+            continue
+        st = lib().dpl_tap_conv_tf32(gp.data_ptr(), plan.q_total, wd.data_ptr(), t, dx.data_ptr(), plan.n, co, ci,
+                                     plan.h, plan.w, plan.hp, plan.wp, plan.origin, plan.stride, a, b, len(taps),
+                                     _ints(shifts), _ints(taps), 0, _err_flag(gp.device).data_ptr(), _stream())
+        _unsupported(st, "dpl_tap_conv_tf32")
+        _count()
+    return dx
+
+
+def dwconv2d_wgrad(x, go, k, stride, pad, out=None):
+    """Depthwise weight gradient dW [C][1][k][k], exact fp32."""
+    n, c, hh, ww = x.shape
+    ho, wo = go.shape[2], go.shape[3]
+    gw = torch.empty((c, 1, k, k), dtype=torch.float32, device=x.device) if out is None else out
+    st = lib().dpl_dwconv2d_wgrad_f32(x.data_ptr(), go.data_ptr(), gw.data_ptr(), n, c, hh, ww, k, int(stride),
+                                      int(pad), ho, wo, _stream())
+    _unsupported(st, "dpl_dwconv2d_wgrad_f32")
+    _count()
+    return gw
+
+
+def dwconv2d_dgrad(go, w, in_hw, stride, pad, out=None):
+    """Depthwise data gradient dX [n][C][H][W], exact fp32."""
+    n, c, ho, wo = go.shape
+    k = int(w.shape[2])
+    hh, ww = in_hw
+    gx = torch.empty((n, c, hh, ww), dtype=torch.float32, device=go.device) if out is None else out
+    st = lib().dpl_dwconv2d_dgrad_f32(go.data_ptr(), w.data_ptr(), gx.data_ptr(), n, c, hh, ww, k, int(stride),
+                                      int(pad), ho, wo, _stream())
+    _unsupported(st, "dpl_dwconv2d_dgrad_f32")
+    _count()
+    return gx
+
+
+def conv_im2col_wgrad(x, go, kernel, stride, pad, scratch=None):
+    """Weight gradient of a convolution with very few input channels (the stem): im2col staging copy, then
+    dW[co][k] = sum_img dY[img][co][px] x cols[img][px][k] on the tcgen05 tile (batch folded into K)."""
+    n, c, hh, ww = x.shape
+    kh, kw = kernel
+    co, ho, wo = go.shape[1], go.shape[2], go.shape[3]
+    k = c * kh * kw
+    k_pad = (k + 3) // 4 * 4
+    px = ho * wo
+    need = n * px * k_pad
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(need, dtype=torch.float32, device=x.device)
+    st = lib().dpl_im2col_f32(x.data_ptr(), scratch.data_ptr(), n, c, hh, ww, kh, kw, int(stride), int(pad), ho, wo,
+                              k_pad, _stream())
+    _unsupported(st, "dpl_im2col_f32")
+    _count()
+    dw = torch.zeros((co, k_pad), dtype=torch.float32, device=x.device)
+    tiles = ((co + 127) // 128) * ((k_pad + 127) // 128)
+    split = max(1, min(n, 296 // max(tiles, 1)))
+    gemm_tf32(go, 0, px, co * px, scratch, 1, k_pad, px * k_pad, dw, k_pad, 0, co, k_pad, px, batch=n,
+              fold_batch=True, split_k=split)
+    return dw[:, :k].reshape(co, c, kh, kw)

@@ -5,14 +5,14 @@ dozens of small kernels per iteration. Here a layer is a bundle of device buffer
 iteration is a fixed sequence of launches with no autograd graph:
 
     K6 weight   W_soft = clamp(floor(W/s) + h(alpha), qmin, qmax) * s        (libdpl_b200)
-    conv / gemm forward                                                      (cuDNN/cuBLAS stand-in)
+    conv / gemm forward                                      (libdpl_b200: tcgen05 TF32 tiles, see _classify)
     K6 epilogue relu [+ drop-fakequant], or fused L2 loss + dL/do at the block end (libdpl_b200)
-    conv / gemm weight-gradient (+ data-gradient inside a block)            (cuDNN/cuBLAS stand-in)
+    conv / gemm weight-gradient (+ data-gradient inside a block)                  (libdpl_b200)
     K6 step     dL/dalpha (+ regulariser) and Adam on alpha, fused            (libdpl_b200)
 
-STAND-IN NOTICE: the dense contraction is issued through torch.ops.aten.convolution /
-convolution_backward (true fp32); a tcgen05 implicit-GEMM tile is the planned replacement
-(DESIGN.md, "what comes next").
+Every layer of both model families of BASELINE.json (ResNet-50, MobileNetV2) runs its contraction and both
+gradients on libdpl_b200 kernels; torch / cuDNN remains only for layer types neither family contains
+(ConvTranspose, grouped or dilated convolutions), announced by a warning.
 """
 import os
 
@@ -107,57 +107,126 @@ class AdaQLayer:
     def _w_for_op(self, w):
         return w.transpose(0, 1) if self.type == 'ConvTranspose' else w
 
-    # ---- forward / backward of the dense op (stand-in: cuDNN / cuBLAS, true fp32) --------
-    def _tensor_core_ok(self, x):
-        """tcgen05 TF32 tile (libdpl_b200 dpl_gemm_tf32) for the shapes TMA can address: 1x1
-        stride-1 ungrouped convolutions with C_in and H*W multiples of 4, and Gemm layers with
-        K a multiple of 4. TF32 is what the reference's torch conv uses by default
-        (cudnn.allow_tf32 = True). DPL_TCGEN05=0 keeps everything on the fp32 library path."""
-        if os.environ.get("DPL_TCGEN05", "1") == "0":
-            return False
-        if getattr(self, "_tc_disabled", False):
-            return False
-        if self.type == 'Gemm':   # K and the output width are leading dimensions of TMA operands
-            return (x.dim() == 2 and x.shape[1] % 4 == 0 and self.weight.shape[0] % 4 == 0
-                    and x.is_contiguous())
-        if self.type != 'Conv' or x.dim() != 4 or not x.is_contiguous():
-            return False
-        k = self.weight.shape[2:]
-        return (list(k) == [1, 1] and self.stride == [1, 1] and self.padding == [0, 0]
-                and self.dilation == [1, 1] and self.groups == 1 and x.shape[1] % 4 == 0
-                and (x.shape[2] * x.shape[3]) % 4 == 0)
+    # ---- forward / backward of the dense op: libdpl_b200 only for both model families ---------------
+    def _classify(self, x):
+        """Which libdpl_b200 contraction serves this layer (ada_quant_layer.py:224-244 is F.conv2d / F.linear /
+        F.conv_transpose2d on cuDNN / cuBLAS):
+          'gemm'  Gemm on the tcgen05 TF32 tile                         (dpl_gemm_tf32)
+          'c1x1'  1x1 stride-1 convolution straight from NCHW           (dpl_gemm_tf32)
+          'taps'  3x3 (stride 1 / 2) and the other 1x1 convolutions on the tap-table TF32 kernels
+                  (dpl_tap_conv_tf32 / dpl_tap_wgrad_tf32) over channel-last staging copies
+          'dw'    depthwise 3x3 / 5x5, exact fp32 on the FMA pipe        (dpl_dwconv2d_*)
+          'stem'  few input channels (3-channel stem): direct fp32 forward, im2col + tcgen05 weight gradient
+          'lib'   anything else (ConvTranspose, grouped, dilated, ... - in neither model family of
+                  BASELINE.json): torch / cuDNN, announced once; DPL_STRICT_NATIVE=1 raises instead.
+        TF32 is what the reference's torch conv uses by default (cudnn.allow_tf32 = True).
+        DPL_TCGEN05=0 keeps everything on the library path (debugging only)."""
+        if os.environ.get("DPL_TCGEN05", "1") == "0" or not x.is_contiguous():
+            return 'lib'
+        if self.type == 'Gemm':
+            ok = x.dim() == 2 and x.shape[1] % 4 == 0 and self.weight.shape[0] % 4 == 0
+            return 'gemm' if ok else 'lib'
+        if self.type != 'Conv' or x.dim() != 4 or self.dilation != [1, 1]:
+            return 'lib'
+        co, cig, kh, kw = self.weight.shape
+        ci = x.shape[1]
+        if kh != kw or self.stride[0] != self.stride[1] or self.padding[0] != self.padding[1]:
+            return 'lib'
+        pads = list(self.node.attrs.get("pads", [0, 0, 0, 0]))
+        if pads[:2] != pads[2:]:
+            return 'lib'
+        k, st, pd = kh, self.stride[0], self.padding[0]
+        if self.groups == 1:
+            if k == 1 and st == 1 and pd == 0 and ci % 4 == 0 and (x.shape[2] * x.shape[3]) % 4 == 0:
+                return 'c1x1'
+            if ((k, pd) in ((3, 1), (1, 0))) and st in (1, 2) and ci % 4 == 0 and co % 4 == 0:
+                return 'taps'
+            if ci * k * k <= 256 and (k, st) in ((7, 2), (3, 2), (3, 1), (5, 2), (5, 1)):
+                return 'stem'
+            return 'lib'
+        if self.groups == ci == co and cig == 1 and k in (3, 5):
+            return 'dw'
+        return 'lib'
+
+    def _lib_notice(self):
+        if os.environ.get("DPL_STRICT_NATIVE", "0") == "1":
+            raise RuntimeError("layer %s (%s) has no libdpl_b200 contraction" % (self.node.name, self.type))
+        if not getattr(AdaQLayer, "_lib_warned", False):
+            AdaQLayer._lib_warned = True
+            from ..utils import logger
+            logger.warning("%s: layer shape outside the libdpl_b200 contraction kernels, using torch / cuDNN"
+                           % self.node.name)
 
     def dense_forward(self, x, w):
-        self._tc = self._tensor_core_ok(x)
-        if self._tc:
-            try:
-                if self.type == 'Gemm':
-                    return K.linear_forward(x, w, self.bias)
-                return K.conv1x1_forward(x, w.view(w.shape[0], w.shape[1]), self.bias)
-            except K.GemmUnsupported:     # e.g. a mis-aligned slice: keep this layer on the library path
-                self._tc = False
-                self._tc_disabled = True
+        kind = self._classify(x) if not getattr(self, "_tc_disabled", False) else 'lib'
+        try:
+            if kind == 'gemm':
+                y = K.linear_forward(x, w, self.bias)
+            elif kind == 'c1x1':
+                y = K.conv1x1_forward(x, w.view(w.shape[0], w.shape[1]), self.bias)
+            elif kind == 'taps':
+                plan = self._plan(x)
+                self._wf, self._wd = K.taps_layout(w, True, True, getattr(self, "_wf", None),
+                                                   getattr(self, "_wd", None))
+                self._xp = K.recon_stage_input(x, plan, getattr(self, "_xp", None))
+                y = K.recon_conv_forward(self._xp, plan, self._wf, self.bias)
+            elif kind == 'dw':
+                y = K.dwconv2d_forward(x, w, self.bias, self.stride[0], self.padding[0])
+            elif kind == 'stem':
+                y = K.conv_direct_forward(x, w, self.bias, self.stride[0], self.padding[0])
+        except K.GemmUnsupported:     # e.g. a mis-aligned slice: keep this layer on the library path
+            kind = 'lib'
+            self._tc_disabled = True
+        self._kind = kind
+        if kind != 'lib':
+            return y
+        self._lib_notice()
         if self.type == 'Gemm':
             return torch.nn.functional.linear(x, w, self.bias)
         return torch.ops.aten.convolution(x, self._w_for_op(w), self.bias, self.stride, self.padding,
                                           self.dilation, self.type == 'ConvTranspose',
                                           self.output_padding, self.groups)
 
+    def _plan(self, x):
+        key = tuple(x.shape)
+        plan = getattr(self, "_plan_cache", {}).get(key)
+        if plan is None:
+            plan = K.ReconConvPlan(x.shape[0], x.shape[2], x.shape[3], self.weight.shape[2], self.stride[0],
+                                   self.padding[0])
+            self._plan_cache = {key: plan}
+        return plan
+
     def dense_backward(self, x, w, go, need_dx):
-        if getattr(self, "_tc", False):
+        """-> (dL/dx or None, dL/dw) for the forward that dense_forward just ran on the same x."""
+        kind = getattr(self, "_kind", 'lib')
+        if kind == 'gemm':
+            return (K.linear_dgrad(go, w) if need_dx else None), K.linear_wgrad(go, x)
+        if kind == 'c1x1':
+            w2 = w.view(w.shape[0], w.shape[1])
+            gw = K.conv1x1_wgrad(go, x).view_as(w)
+            return (K.conv1x1_dgrad(go, w2) if need_dx else None), gw
+        if kind == 'taps':
+            plan = self._plan(x)
+            self._gp = K.recon_stage_grad(go, plan, getattr(self, "_gp", None))
+            gw = K.recon_conv_wgrad(self._gp, self._xp, plan, w.shape[0], w.shape[1])
+            gx = K.recon_conv_dgrad(self._gp, plan, self._wd) if need_dx else None
+            return gx, gw
+        if kind == 'dw':
+            k, st, pd = w.shape[2], self.stride[0], self.padding[0]
+            gw = K.dwconv2d_wgrad(x, go, k, st, pd)
+            gx = K.dwconv2d_dgrad(go, w, (x.shape[2], x.shape[3]), st, pd) if need_dx else None
+            return gx, gw
+        if kind == 'stem' and not need_dx:
             try:
-                if self.type == 'Gemm':
-                    return (K.linear_dgrad(go, w) if need_dx else None), K.linear_wgrad(go, x)
-                w2 = w.view(w.shape[0], w.shape[1])
-                gw = K.conv1x1_wgrad(go, x).view_as(w)
-                return (K.conv1x1_dgrad(go, w2) if need_dx else None), gw
-            except K.GemmUnsupported:
-                self._tc = False
-                self._tc_disabled = True
+                return None, K.conv_im2col_wgrad(x, go, (w.shape[2], w.shape[3]), self.stride[0], self.padding[0])
+            except K.GemmUnsupported:      # output plane not a multiple of 4 pixels (TMA stride rule)
+                pass
         if self.type == 'Gemm':
             gw = go.t() @ x
             gx = go @ w if need_dx else None
             return gx, gw
+        if kind != 'lib':
+            self._lib_notice()
         wt = self._w_for_op(w)
         gx, gw, _ = torch.ops.aten.convolution_backward(
             go, x, wt, None, self.stride, self.padding, self.dilation, self.type == 'ConvTranspose',

@@ -12,6 +12,7 @@ from ..utils import logger
 from .ada_quant_layer import AdaQLayer, adaround_reg
 from .learning import learning_round_mask
 from .utils import LEARNABLE_LAYER_TYPES, follow_relu, get_quant_tensor, update_weight
+from .weight_equalization import node_has_equalized
 
 
 def quantised_input_name(graph_q, tensor):
@@ -46,6 +47,9 @@ def adaround(graph_ori, graph, act_clip_val, weight_clip_val, args):
     qw_param = platform_setting_table[args.deploy]['qw_params']
     for node in graph_ori.graph.node:
         if node.name in args.skip_layers or node.op_type not in LEARNABLE_LAYER_TYPES:
+            continue
+        # an equalised layer's output no longer matches graph_ori's: it cannot be mimicked (adaround.py:35-36)
+        if getattr(args, "we", False) and node_has_equalized(graph, node):
             continue
         if dist_helper.get_rank() == 0:
             logger.info("Adaround for: {}".format(node.name))

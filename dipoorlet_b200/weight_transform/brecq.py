@@ -12,6 +12,7 @@ from ..utils import logger
 from .ada_quant_layer import AdaQLayer, adaround_reg
 from .adaround import quantised_input_name, shard
 from .learning import learning_round_mask
+from .weight_equalization import node_has_equalized
 from .utils import (LEARNABLE_LAYER_TYPES, follow_relu, following_relu, get_block_from_first,
                     get_quant_tensor, update_weight)
 
@@ -34,6 +35,11 @@ def brecq(graph_ori, graph, act_clip_val, weight_clip_val, args):
                 or node.name in already:
             continue
         block = get_block_from_first(graph, node, args)
+        # an equalised layer cannot close a block: its output differs from graph_ori's (brecq.py:38-41)
+        if getattr(args, "we", False) and node_has_equalized(graph, block[-1]):
+            block = block[:-1]
+            if not block:       # the reference would index an empty list here; skipping is the only sane reading
+                continue
         if dist_helper.get_rank() == 0:
             logger.info("{} for: {}".format(head, ' '.join(n.name for n in block)))
         already.extend(n.name for n in block)

@@ -332,6 +332,35 @@ int dpl_maxpool2d_f32(const float* d_x, float* d_y, uint64_t planes, int H, int 
 int dpl_global_avgpool_f32(const float* d_x, float* d_y, uint64_t planes, uint64_t hw, float* d_blob_min,
                            float* d_blob_max, void* stream);
 
+/* ---- K6 dense contraction for k x k / strided / depthwise convolutions (single-pass TF32) ----------------
+ * Replaces F.conv2d and the weight / data gradients autograd derives from it inside AdaQLayer.forward /
+ * learning_round_mask (weight_transform/ada_quant_layer.py:224-244, adaround.py:119-135,
+ * brecq.py:163-186), which torch runs on cuDNN with TF32 allowed. All three contractions work on the
+ * channel-last, zero-bordered staging copies written by dpl_pad_plane_f32 (Xp of the layer input, Gp of
+ * the output gradient), in which a filter tap is a row shift.
+ *
+ * dpl_tap_conv_tf32 (forward, and data gradient with the roles of the channels swapped):
+ *   Y[img][cn][hq*os + oa][wq*os + ob] = bias[cn] + sum_tap sum_ck Wt[tap_w[tap]][cn][ck] * Xp[q + tap_shift[tap]][ck]
+ *   q = img*Hp*Wp + (hq + origin)*Wp + (wq + origin); points whose pixel is outside H x W are dropped.
+ *   ck must be a multiple of 4 (else DPL_E_UNSUPPORTED). tap_shift / tap_w: host arrays of n_taps <= 9.
+ * dpl_tap_wgrad_tf32: dW[co][ci][tap_col[t]] = sum_q Gp[q][co] * Xp[q + tap_shift[t]][ci]; the whole batch is
+ *   the K dimension, split over CTAs that add into the zeroed d_dw [c_out][c_in][t_full].
+ * dpl_taps_layout_f32: w [c_out][c_in][T] -> d_wf [T][c_out][c_in] and / or d_wd [T][c_in][c_out].
+ * dpl_dwconv2d_wgrad_f32 / _dgrad_f32: depthwise (group = channels) gradients on the FMA pipe, exact fp32,
+ *   k in {3, 5}; d_gw [C][k][k] and d_gx [n_img][C][H][W] are fully overwritten. */
+int dpl_tap_conv_tf32(const float* d_xp, long long total_rows, const float* d_w_taps, int n_w_taps,
+                      float* d_y, int n_img, int ck, int cn, int H, int W, int Hp, int Wp, int origin,
+                      int out_stride, int out_a, int out_b, int n_taps, const int* tap_shift,
+                      const int* tap_w, const float* d_bias, int* d_error_flag, void* stream);
+int dpl_tap_wgrad_tf32(const float* d_gp, long long q_total, const float* d_xp, long long x_rows,
+                       float* d_dw, int c_out, int c_in, int t_full, int n_taps, const int* tap_shift,
+                       const int* tap_col, int* d_error_flag, void* stream);
+int dpl_taps_layout_f32(const float* d_w, float* d_wf, float* d_wd, int c_out, int c_in, int T, void* stream);
+int dpl_dwconv2d_wgrad_f32(const float* d_x, const float* d_gy, float* d_gw, int n_img, int C, int H, int W,
+                           int k, int stride, int pad, int Ho, int Wo, void* stream);
+int dpl_dwconv2d_dgrad_f32(const float* d_gy, const float* d_w, float* d_gx, int n_img, int C, int H, int W,
+                           int k, int stride, int pad, int Ho, int Wo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
