@@ -47,6 +47,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hist", choices=["hist", "finetune"],
+                    help="hist = BASELINE.json configs[1] (the headline, default); finetune = the brecq + drop "
+                         "rounding loop of configs[4] on ResNet-50's blocks (see run_finetune)")
+    ap.add_argument("--ft-images", type=int, default=256, help="finetune: calibration images per GPU")
+    ap.add_argument("--ft-epoch", type=int, default=2, help="finetune: --ada_epoch (the CLI default 5000 is days)")
+    ap.add_argument("--ft-model", default="r50", choices=["r50", "mbv2"])
+    ap.add_argument("--ft-algo", default="brecq", choices=["brecq", "adaround"])
     ap.add_argument("--images", type=int, default=IMAGES_PER_GPU, help="images per GPU")
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--hist-variant", type=int, default=0)
@@ -357,9 +364,256 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------ rounding finetune (configs[3] / configs[4])
+FT_METRIC = "rounding-finetune iterations/sec (ada_bs 64)"
+
+
+def _ft_blocks(model_name, algo):
+    """The reference's learnable blocks (brecq.py:33-37: get_block_from_first; adaround: single layers) of the
+    real model graph: [(names, [dict(node, weight, bias, relu)], in_shape)]."""
+    from dipoorlet_b200 import workloads as W
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.weight_transform.utils import LEARNABLE_LAYER_TYPES, follow_relu, get_block_from_first
+    model = W.build_resnet50(seed=0) if model_name == "r50" else W.build_mobilenetv2(seed=0)
+    graph = ONNXGraph(model, "/tmp/dpl_bench_ft", "trt")
+    args = make_args(deploy="trt", output_dir="/tmp/dpl_bench_ft")
+    blocks, done = [], set()
+    for node in graph.graph.node:
+        if node.op_type not in LEARNABLE_LAYER_TYPES or node.name in done:
+            continue
+        block = get_block_from_first(graph, node, args) if algo == "brecq" else [node]
+        done.update(n.name for n in block)
+        layers = []
+        for n in block:
+            layers.append(dict(node=n, weight=graph.get_initializer(n.input[1]),
+                               bias=graph.get_initializer(n.input[2]) if len(n.input) == 3 else None,
+                               relu=follow_relu(graph, n)))
+        blocks.append(([n.name for n in block], layers, list(graph.get_tensor_shape(block[0].input[0]))))
+    return blocks
+
+
+def _ft_conv(x, lay):
+    """fp32 evaluation of one layer with torch (set-up of the synthetic targets only, not timed)."""
+    import torch
+    import torch.nn.functional as F
+    n, w = lay["node"], lay["w_t"]
+    if n.op_type == "Gemm":
+        y = F.linear(x, w, lay["b_t"])
+    else:
+        a = n.attrs
+        y = F.conv2d(x, w, lay["b_t"], a.get("strides", [1, 1]), a.get("pads", [0, 0, 0, 0])[:2],
+                     a.get("dilations", [1, 1]), a.get("group", 1))
+    return torch.relu(y) if lay["relu"] else y
+
+
+def _ft_setup(blocks, n_img, dev, seed):
+    """Synthetic block inputs (post-ReLU-like), their fake-quantised copies, fp targets and the weight /
+    activation quantisation parameters (trt: symmetric int8, per-channel weights)."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(seed)
+    out = []
+    for names, layers, in_shape in blocks:
+        shape = [n_img] + in_shape[1:]
+        fp_in = torch.randn(shape, device=dev, generator=g)
+        if len(shape) == 4 and shape[1] > 3:
+            fp_in = torch.relu(fp_in)
+        s_in = float(fp_in.abs().max()) / 127
+        q_in = torch.clamp(torch.round(fp_in / s_in), -127, 127) * s_in
+        t = fp_in
+        for lay in layers:
+            lay["w_t"] = torch.from_numpy(lay["weight"]).to(dev)
+            lay["b_t"] = None if lay["bias"] is None else torch.from_numpy(lay["bias"]).to(dev)
+            chunks = [_ft_conv(t[i:i + 64], lay) for i in range(0, n_img, 64)]
+            t = torch.cat(chunks)
+            w = lay["w_t"]
+            lay["scale"] = (w.abs().reshape(w.shape[0], -1).amax(dim=1) / 127).clamp_min(1e-12).contiguous()
+            lay["qi"] = (float(t.abs().max()) / 127, -127.0, 127.0)
+        out.append((names, layers, q_in, fp_in, t))
+    return out
+
+
+def run_finetune(args):
+    """--workload finetune: one "step" = the brecq + drop (or adaround) learned-rounding loop with --ada_epoch
+    E over EVERY learnable block of the model, ada_bs 64, on synthetic block inputs of the real shapes
+    resident in HBM. value = optimiser iterations/s summed over ranks; at N > 1 each rank has its own images
+    and the weight gradients are averaged per iteration (DDP semantics, brecq.py:164)."""
+    import torch
+    import torch.distributed as dist
+    from dipoorlet_b200 import dist_helper, kernels as K
+    from dipoorlet_b200.weight_transform.ada_quant_layer import AdaQLayer, adaround_reg
+    from dipoorlet_b200.weight_transform.learning import learning_round_mask
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rank, local_rank, world = dist_helper.init_from_env()
+        dev = torch.device("cuda", local_rank)
+        torch.cuda.set_device(dev)
+        if world > 1:
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    os.environ.setdefault("DPL_STRICT_NATIVE", "1")      # a cuDNN / cuBLAS contraction would be a bug here
+    n_img, bs = args.ft_images, 64
+    drop = args.ft_algo == "brecq"
+    data = _ft_setup(_ft_blocks(args.ft_model, args.ft_algo), n_img, dev, seed=100 + rank)
+    n_batches = -(-n_img // bs)
+    per_block = []
+
+    def one_pass(record=None):
+        iters = 0
+        for bi, (names, layers, q_in, fp_in, tgt) in enumerate(data):
+            epochs = args.ft_epoch * len(layers)
+            ls = [AdaQLayer(l["node"], l["w_t"], l["b_t"], l["scale"], -127, 127, l["relu"], qi=l["qi"],
+                            acti_quant=drop, device=dev) for l in layers]
+            reg = adaround_reg(epochs * n_batches)
+            if record is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            learning_round_mask(ls, q_in, tgt, reg, bs, epochs, fp_in=fp_in, drop=drop, log_every=10 ** 9, seed=bi)
+            if record is not None:
+                e1.record()
+                record.append((names, epochs * n_batches, e0, e1))
+            iters += epochs * n_batches
+        return iters
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_pass()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    sync_all()
+    l0 = K.launches()
+    t0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    iters = 0
+    rec = []
+    for _ in range(args.steps):
+        iters += one_pass(rec)
+    e1.record()
+    sync_all()
+    t1 = time.time()
+    launches = K.launches() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    K.gemm_check_errors()
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    agg = {}
+    for names, n_it, a, b in rec:
+        d = agg.setdefault(" ".join(names), [0, 0.0])
+        d[0] += n_it
+        d[1] += a.elapsed_time(b)
+    per_block = [{"block": k, "iterations": v[0], "ms_per_iteration": v[1] / v[0]} for k, v in agg.items()]
+    line = {"metric": FT_METRIC, "value": iters * world / (ms / 1e3), "unit": "iterations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": "%s %s%s, every learnable block, %d synthetic block inputs per GPU, --ada_bs 64 "
+                                   "--ada_epoch %d -D trt" % ("ResNet-50" if args.ft_model == "r50" else "MobileNetV2",
+                                                              args.ft_algo, " --drop" if drop else "", n_img,
+                                                              args.ft_epoch),
+                       "blocks": len(data), "iterations_per_step": iters // args.steps,
+                       "l2": "block inputs of %d images exceed L2 for the large feature maps; small ones are "
+                             "L2 resident as in the real job" % n_img,
+                       "gradient_reduction": ("peer (NVLink, in the step kernel)" if os.environ.get(
+                           "DPL_PEER_ALLREDUCE") == "1" else "NCCL all-reduce per layer") if world > 1 else "none"},
+            "clocks": clocks, "gpu_launches": launches, "per_block": per_block}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_finetune_reference(args):
+    """--workload finetune --impl reference: the reference's own loop for this path — torch autograd + cuDNN
+    (TF32 allowed, torch's default) + torch.optim.Adam, restated op for op in oracle/adaround.py (pinned
+    bit-exactly against the reference's rounded weights on CPU) — on the same GPU, same blocks, same data."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import adaround as OA
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    n_img, bs = args.ft_images, 64
+    drop = args.ft_algo == "brecq"
+    data = _ft_setup(_ft_blocks(args.ft_model, args.ft_algo), n_img, dev, seed=100)
+    n_batches = -(-n_img // bs)
+
+    def one_pass(record=None):
+        iters = 0
+        for names, layers, q_in, fp_in, tgt in data:
+            epochs = args.ft_epoch * len(layers)
+            ls = []
+            for l in layers:
+                n = l["node"]
+                attrs = dict(strides=n.attrs.get("strides", [1, 1]), pads=n.attrs.get("pads", [0, 0, 0, 0]),
+                             dilations=n.attrs.get("dilations", [1, 1]), group=n.attrs.get("group", 1))
+                w = l["w_t"]
+                view = [-1] + [1] * (w.dim() - 1)
+                qi = tuple(torch.tensor(v, device=dev) for v in l["qi"])
+                ls.append(OA.Layer(n.op_type, attrs, w, l["b_t"], l["scale"].view(view),
+                                   torch.full(view, -127.0, device=dev).expand(w.shape[0], *view[1:]),
+                                   torch.full(view, 127.0, device=dev).expand(w.shape[0], *view[1:]),
+                                   l["relu"], qi=qi, acti_quant=drop))
+            if record is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            OA.learn(ls, q_in, tgt, epochs * n_batches, bs, epochs, fp_in=fp_in, drop=drop)
+            if record is not None:
+                e1.record()
+                record.append((names, epochs * n_batches, e0, e1))
+            iters += epochs * n_batches
+        return iters
+
+    for _ in range(args.warmup):
+        one_pass()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    iters, rec = 0, []
+    for _ in range(args.steps):
+        iters += one_pass(rec)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    agg = {}
+    for names, n_it, a, b in rec:
+        d = agg.setdefault(" ".join(names), [0, 0.0])
+        d[0] += n_it
+        d[1] += a.elapsed_time(b)
+    value = iters / (ms / 1e3)
+    line = {"impl": "reference", "metric": FT_METRIC, "value": value, "unit": "iterations/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 conv / fp32 linear (torch defaults)",
+            "data": "synthetic",
+            "config": {"workload": "same blocks and data as the ours arm; torch autograd + cuDNN + torch.optim.Adam "
+                                   "on ONE GPU (the reference's loop, adaround.py:119-144 / brecq.py:158-200)",
+                       "iterations_per_step": iters // args.steps},
+            "per_block": [{"block": k, "iterations": v[0], "ms_per_iteration": v[1] / v[0]} for k, v in agg.items()]}
+    print(json.dumps(line))
+
+
 def main():
     args = parse()
-    if args.impl == "reference":
+    if args.workload == "finetune":
+        (run_finetune_reference if args.impl == "reference" else run_finetune)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

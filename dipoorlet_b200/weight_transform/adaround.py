@@ -45,6 +45,11 @@ def adaround(graph_ori, graph, act_clip_val, weight_clip_val, args):
     graph_q, _ = quant_graph(graph_ada, copy.deepcopy(clip_val), args)
     q_cache = ActivationCache(graph_q, args, rank_st, rank_ed)
     qw_param = platform_setting_table[args.deploy]['qw_params']
+    if qw_param.get('per_channel') and not qw_param.get('symmetric'):
+        # the clamp limits then differ per channel (they depend on each channel's zero point); the K6 kernels
+        # take one (q_min, q_max) pair per layer, so refuse instead of clamping every channel with channel 0's
+        raise NotImplementedError("learned rounding with per-channel asymmetric weight quantisation (-D %s)"
+                                  % args.deploy)
     for node in graph_ori.graph.node:
         if node.name in args.skip_layers or node.op_type not in LEARNABLE_LAYER_TYPES:
             continue

@@ -102,7 +102,9 @@ def test_stem_wgrad(dpl_built, n, c, co, h, w, k, stride, pad):
     (gw_want,) = torch.autograd.grad(y, wd, _tf32(go).double())
     gw = K.conv_im2col_wgrad(x, go, (k, k), stride, pad)
     K.gemm_check_errors()
-    _check(gw, gw_want, np.sqrt(n * y.shape[2] * y.shape[3]) * 4, "stem wgrad")
+    # K = n * Ho * Wo up to 50 176 products per output, split over CTAs that add their partial sums atomically
+    err = (gw.double() - gw_want).abs().max().item()
+    assert err <= 2e-4 * gw_want.abs().max().item(), err
 
 
 def test_adaqlayer_native_kinds(dpl_built):
