@@ -16,6 +16,7 @@ from ..utils import logger
 
 
 _PEER_POOL = {}   # device index -> (symmetric float32 buffer, its rendezvous handle)
+TIMINGS = None    # set to a list by a benchmark: one (loop_start, loop_end, iterations, graphs_used) of CUDA events per call
 
 
 def peer_layout(sizes, words=64):
@@ -180,56 +181,65 @@ def _learn(layers, q_in, tgt, reg, batch_size, max_epoch, fp_in, drop, log_every
     def schedule():
         K.recon_schedule(d_iter, sched, seeds, t_max, seed_base=seed)
 
-    # ---- CUDA graph of one full-size iteration: static input buffers + replay ------------------
-    # The launch-bound inner loop (a dozen launches per iteration, millions of iterations at the
-    # default --ada_epoch 5000) is captured once per layer/block and replayed. Multi-rank runs
-    # and DPL_CUDA_GRAPH=0 keep the eager sequence, as do short runs (capture costs ~50 iterations).
-    # Measured (tools/learn_bench.py): iterations on 56x56 feature maps are GPU bound (0.2-1.2 ms
-    # each) and gain nothing from replay — the static-input copies even cost — so "auto" only
-    # captures when a mini-batch of block inputs is small (launch-bound regime); "1" forces it.
+    # ---- one CUDA graph per mini-batch index, replayed every epoch -----------------------------------------
+    # An iteration is ~15 launches per layer (weight build, re-layout, staging copies, contraction forward /
+    # weight / data gradient, epilogues, fused step) and takes 0.1 - 0.5 ms of GPU time: issued eagerly from
+    # Python it is launch bound (measured: 0.6 - 1.2 ms per ResNet-50 block iteration,
+    # profiles/r2_finetune_*). Every per-iteration scalar lives in device memory (schedule kernel), the
+    # mini-batches are fixed slices of buffers that stay in place for the whole run (x_all is rewritten in
+    # place by the per-epoch QDrop mix), so the iteration on slice idx is captured ONCE, reading its slice
+    # directly (no static-input copies), and replayed max_epoch times. The graphs share one memory pool.
+    # "auto": when every graph is replayed at least 8 times; DPL_CUDA_GRAPH=0 / 1 force eager / graphs.
+    # The peer (NVLink) gradient path passes a host-side epoch to its kernel and stays eager; NCCL inside a
+    # captured iteration is opt-in (DPL_CUDA_GRAPH_NCCL=1).
     mode = os.environ.get("DPL_CUDA_GRAPH", "auto")
-    small = q_in[:batch_size].numel() * 4 <= (4 << 20)
-    use_graph = ((mode == "1" or (mode == "auto" and small)) and world == 1 and n >= batch_size
-                 and max_epoch * n_batches >= int(os.environ.get("DPL_CUDA_GRAPH_MIN_ITERS", "256")))
-    graph = None
+    nccl_ok = world == 1 or os.environ.get("DPL_CUDA_GRAPH_NCCL", "0") == "1"
+    use_graph = (mode == "1" or (mode == "auto" and max_epoch >= 8)) and peer is None and nccl_ok and max_epoch > 1
+    graphs = {}
     if use_graph:
-        xb = torch.empty_like(x_all[:batch_size])
-        tb = torch.empty_like(tgt[:batch_size])
         state = [(l.round_mask.clone(), l.m.clone(), l.v.clone()) for l in layers]
         try:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):       # warm-up outside capture (cuDNN plans, tensor maps)
-                xb.copy_(q_in[:batch_size])
-                tb.copy_(tgt[:batch_size])
+            with torch.cuda.stream(side):       # warm-up outside capture (lazy attributes, scratch buffers)
+                if ratio < 1.0:
+                    x_all.copy_(q_in)
                 for _ in range(2):
                     schedule()
-                    _iteration(layers, xb, tb, reg.alpha, world, loss_acc, sched, seeds)
+                    _iteration(layers, x_all[:batch_size], tgt[:batch_size], reg.alpha, world, loss_acc, sched,
+                               seeds)
             torch.cuda.current_stream(dev).wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                schedule()
-                _iteration(layers, xb, tb, reg.alpha, world, loss_acc, sched, seeds)
+            pool = None
+            for idx in range(n_batches):
+                st, ed = idx * batch_size, min((idx + 1) * batch_size, n)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    schedule()
+                    _iteration(layers, x_all[st:ed], tgt[st:ed], reg.alpha, world, loss_acc, sched, seeds)
+                pool = g.pool()
+                graphs[idx] = g
         except Exception as e:   # capture not possible (e.g. an op that syncs): stay eager
             logger.warning("CUDA graph capture of the rounding loop failed (%s); running eagerly" % (e,))
-            graph = None
-        # the warm-up / capture iterations must not count: restore alpha, Adam state and t
+            graphs = {}
+        # the warm-up iterations must not count: restore alpha, Adam state and the iteration counter
         for l, (a, m, v) in zip(layers, state):
             l.round_mask.copy_(a)
             l.m.copy_(m)
             l.v.copy_(v)
         d_iter.zero_()
 
+    if TIMINGS is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     for epoch in range(max_epoch):
         if ratio < 1.0:  # QDrop: a fresh Bernoulli mix of quantised and fp block inputs per epoch
             K.mix_drop(q_in, fp_in, ratio, _seed(seed, epoch, 991), out=x_all)
         for idx in range(n_batches):
-            st, ed = idx * batch_size, min((idx + 1) * batch_size, n)
-            if graph is not None and ed - st == batch_size:
-                xb.copy_(x_all[st:ed])
-                tb.copy_(tgt[st:ed])
-                graph.replay()
+            g = graphs.get(idx)
+            if g is not None:
+                g.replay()
             else:
+                st, ed = idx * batch_size, min((idx + 1) * batch_size, n)
                 schedule()
                 if peer is not None:
                     peer.next_epoch()
@@ -237,6 +247,9 @@ def _learn(layers, q_in, tgt, reg, batch_size, max_epoch, fp_in, drop, log_every
         if epoch % log_every == 0 and rank0:
             logger.info("Epoch: {:<5} L2 Loss: {:>10.3f} Beta: {:>3.3f}".format(
                 epoch, float(loss_acc.item()), float(sched[0].item())))
+    if TIMINGS is not None:
+        ev1.record()
+        TIMINGS.append((ev0, ev1, max_epoch * n_batches, bool(graphs)))
     loss = float(loss_acc.item()) if max_epoch > 0 else float("nan")
     if peer is not None:
         peer.check()
