@@ -189,12 +189,15 @@ def _learn(layers, q_in, tgt, reg, batch_size, max_epoch, fp_in, drop, log_every
     # mini-batches are fixed slices of buffers that stay in place for the whole run (x_all is rewritten in
     # place by the per-epoch QDrop mix), so the iteration on slice idx is captured ONCE, reading its slice
     # directly (no static-input copies), and replayed max_epoch times. The graphs share one memory pool.
-    # "auto": when every graph is replayed at least 8 times; DPL_CUDA_GRAPH=0 / 1 force eager / graphs.
+    # Measured (profiles/r2_finetune_eager_vs_graph.json): the eager loop is GPU bound - the launches queue
+    # ahead of the kernels - and replay gains 5 - 8 % per iteration, while capture costs about a second per
+    # block (private pool allocation + instantiation). "auto": graphs when every one of them is replayed at
+    # least 64 times (the CLI default --ada_epoch 5000 is); DPL_CUDA_GRAPH=0 / 1 force eager / graphs.
     # The peer (NVLink) gradient path passes a host-side epoch to its kernel and stays eager; NCCL inside a
     # captured iteration is opt-in (DPL_CUDA_GRAPH_NCCL=1).
     mode = os.environ.get("DPL_CUDA_GRAPH", "auto")
     nccl_ok = world == 1 or os.environ.get("DPL_CUDA_GRAPH_NCCL", "0") == "1"
-    use_graph = (mode == "1" or (mode == "auto" and max_epoch >= 8)) and peer is None and nccl_ok and max_epoch > 1
+    use_graph = (mode == "1" or (mode == "auto" and max_epoch >= 64)) and peer is None and nccl_ok and max_epoch > 1
     graphs = {}
     if use_graph:
         state = [(l.round_mask.clone(), l.m.clone(), l.v.clone()) for l in layers]
