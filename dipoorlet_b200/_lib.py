@@ -76,6 +76,7 @@ SIGNATURES = {
                                ctypes.c_longlong, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp,
                                _c_int, _c_int, _c_vp, _c_vp]),
     "dpl_tf32_residual_f32": (_c_int, [_c_vp, _c_vp, _c_u64, _c_vp]),
+    "dpl_tf32_split_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_u64, _c_vp]),
     "dpl_gemm_tf32x3": (_c_int, [_c_vp, _c_vp, _c_int, ctypes.c_longlong, ctypes.c_longlong, _c_vp, _c_int,
                                  ctypes.c_longlong, ctypes.c_longlong, _c_vp, ctypes.c_longlong,
                                  ctypes.c_longlong, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_int,

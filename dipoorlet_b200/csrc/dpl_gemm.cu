@@ -760,11 +760,30 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   }
 }
 
+__device__ __forceinline__ float tf32_rn_host_side(float x) {   // round to nearest (even) TF32
+  uint32_t u = __float_as_uint(x);
+  u += 0xFFFu + ((u >> 13) & 1u);
+  return __uint_as_float(u & 0xFFFFE000u);
+}
+
+// residual of the truncated pattern (what kind::tf32 reads from raw fp32), rounded to TF32 so that the tensor
+// core reads it exactly
 __global__ void __launch_bounds__(256)
 tf32_residual_kernel(const float* __restrict__ x, float* __restrict__ lo, uint64_t n) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    lo[i] = tf32_residual(x[i]);
+    lo[i] = tf32_rn_host_side(tf32_residual(x[i]));
+}
+
+// unbiased split for weights: hi = RN_tf32(x), lo = RN_tf32(x - hi)
+__global__ void __launch_bounds__(256)
+tf32_split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, uint64_t n) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = x[i], h = tf32_rn_host_side(v);
+    hi[i] = h;
+    lo[i] = tf32_rn_host_side(v - h);
+  }
 }
 
 // ---- 3x3 convolution (stride 1, pad 1) as a shifted-window implicit GEMM, 3xTF32 ----------
@@ -1529,6 +1548,8 @@ int make_map_px(CUtensorMap* map, const float* base, uint64_t hw, uint64_t c_in,
   return 0;
 }
 
+#include "dpl_x3p.cuh"
+
 }  // namespace
 }  // namespace dpl
 
@@ -1644,6 +1665,18 @@ extern "C" int dpl_tf32_residual_f32(const float* d_x, float* d_lo, uint64_t n, 
   return 0;
 }
 
+// Unbiased operand split for weights (done once): hi = RN_tf32(x), lo = RN_tf32(x - hi). Truncating instead
+// (what kind::tf32 does to a raw fp32 pattern) shrinks every product by ~2^-22: 2.8e-7 per layer, compounding.
+extern "C" int dpl_tf32_split_f32(const float* d_x, float* d_hi, float* d_lo, uint64_t n, void* stream) {
+  DPL_REQUIRE(d_x && d_hi && d_lo, "null pointer");
+  if (n == 0) return 0;
+  uint64_t blocks = (n + 1023) / 1024;
+  if (blocks > (uint64_t)sm_count() * 8) blocks = (uint64_t)sm_count() * 8;
+  tf32_split_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_hi, d_lo, n);
+  DPL_LAUNCH_CHECK("tf32_split_kernel");
+  return 0;
+}
+
 // 3xTF32 variant of dpl_gemm_tf32 (fp32-accurate): same operand description plus d_a_lo, the
 // residual of A with A's layout. No batch folding / split-K (forward use only).
 extern "C" int dpl_gemm_tf32x3(const float* d_a, const float* d_a_lo, int a_major, long long lda,
@@ -1696,6 +1729,18 @@ extern "C" int dpl_gemm_tf32x3(const float* d_a, const float* d_a_lo, int a_majo
   dim3 grid((M + kBM - 1) / kBM, (N + kBN - 1) / kBN, (unsigned)batch);
   const size_t smem = (size_t)kStages3 * kStageBytes3 + 1024;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a_major == 0 && b_major == 1 && !p.a_batched && bias_mode != 2 && x3_chunk_iters() > 0) {
+    // 1x1 convolution: persistent kernel with chunked accumulation (dpl_x3p.cuh), any K
+    X3PParams xp;
+    xp.chunk_iters = x3_chunk_iters();
+    xp.g = p;
+    xp.c = ConvParams();
+    const long long total = (long long)grid.x * grid.y * grid.z;
+    int e = launch_x3p<0>(tmA, tmAlo, tmB, xp, total, s);
+    if (e) return e;
+    DPL_LAUNCH_CHECK("x3p_kernel<0>");
+    return 0;
+  }
   if (a_major == 0 && b_major == 1 && !p.a_batched && bias_mode != 2 && K <= x3_persistent_max_k()) {
     // short-K 1x1 convolution: persistent kernel, one CTA per SM
     static bool attr_done_p = false;
@@ -1818,6 +1863,18 @@ extern "C" int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, con
   p.bmax = d_blob_max;
   p.rmin = d_relu_min;
   p.rmax = d_relu_max;
+  if (!taps_ts && x3_chunk_iters() > 0) {
+    // persistent kernel with chunked accumulation (dpl_x3p.cuh)
+    X3PParams xp;
+    xp.chunk_iters = x3_chunk_iters();
+    xp.g = GemmParams();
+    xp.c = p;
+    const long long total = ((q_total + kBM - 1) / kBM) * ((c_out + bn - 1) / bn);
+    int e = launch_x3p<1>(tmW, tmWlo, tmX, xp, total, static_cast<cudaStream_t>(stream));
+    if (e) return e;
+    DPL_LAUNCH_CHECK("x3p_kernel<1>");
+    return 0;
+  }
   if (taps_ts) {
     DPL_REQUIRE((q_total + kBM - 1) / kBM <= 65535, "grid limit (DPL_TAPS_TS)");
     dim3 grid_ts((unsigned)((c_out + kPxBN - 1) / kPxBN), (unsigned)((q_total + kBM - 1) / kBM), 1);

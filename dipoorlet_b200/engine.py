@@ -274,15 +274,15 @@ class Engine:
                 and not any(lo) and not any(hi) and node.attrs.get("group", 1) == 1
                 and x.is_contiguous() and x.shape[1] % 4 == 0 and (x.shape[2] * x.shape[3]) % 4 == 0)
 
-    def _residual(self, name, w2):
-        """TF32 residual of a weight; cached for initializers only (a weight produced by a
-        Q/DQ pair inside the graph is recomputed: it changes whenever its source does)."""
+    def _split(self, name, w2):
+        """(hi, lo) TF32 split of a weight (K.tf32_split); cached for initializers only (a weight produced by
+        a Q/DQ pair inside the graph is recomputed: it changes whenever its source does)."""
         if name not in self.params:
-            return K.tf32_residual(w2.contiguous())
-        lo = self._w_lo.get(name)
-        if lo is None or lo.shape != w2.shape:
-            lo = self._w_lo[name] = K.tf32_residual(w2.contiguous())
-        return lo
+            return K.tf32_split(w2)
+        pair = self._w_lo.get(name)
+        if pair is None or pair[0].shape != w2.shape:
+            pair = self._w_lo[name] = K.tf32_split(w2)
+        return pair
 
     def _taps(self, name, w):
         """Tap-major copy + residual of a filter for dpl_conv_taps_tf32x3 (same caching rule)."""
@@ -331,10 +331,11 @@ class Engine:
                     w2 = w.view(w.shape[0], w.shape[1])
                     out = self._new((x.shape[0], w.shape[0], x.shape[2], x.shape[3]), x)
                     r = self._relu_out(node, out, env)
+                    w_hi, w_lo = self._split(node.input[1], w2)
                     if self.conv1x1_px:
-                        y = K.conv1x1_px_forward_x3(x, w2, self._residual(node.input[1], w2), b, out=out, out_relu=r)
+                        y = K.conv1x1_px_forward_x3(x, w_hi, w_lo, b, out=out, out_relu=r)
                     else:
-                        y = K.conv1x1_forward_x3(x, w2, self._residual(node.input[1], w2), b, out=out, out_relu=r,
+                        y = K.conv1x1_forward_x3(x, w_hi, w_lo, b, out=out, out_relu=r,
                                                  rng=self._rng(node.output[0]),
                                                  rng_relu=self._rng_relu(node) if r is not None else None)
                     self._publish_relu(node, r, env)

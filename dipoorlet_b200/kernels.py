@@ -508,6 +508,18 @@ def tf32_residual(x):
     return lo
 
 
+def tf32_split(x):
+    """(hi, lo) = (RN_tf32(x), RN_tf32(x - hi)): the unbiased operand split of a WEIGHT for the 3xTF32 kernels
+    (computed once). Pass `hi` where the kernels take the weight and `lo` as its residual: truncating the raw
+    pattern instead shrinks every product by ~2^-22, which compounds over ResNet-50's 53 layers."""
+    x = x.contiguous()
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    check(lib().dpl_tf32_split_f32(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream()),
+          "dpl_tf32_split_f32")
+    _count()
+    return hi, lo
+
+
 def gemm_tf32x3(a, a_lo, a_major, lda, a_batch_stride, b, b_major, ldb, b_batch_stride, d, ldd,
                 d_batch_stride, M, N, K, batch=1, bias=None, bias_mode=0, relu=False, d_relu=None, rng=None,
                 rng_relu=None):
@@ -574,11 +586,11 @@ def linear_forward_x3(x, w, w_lo=None, bias=None, out=None, rng=None):
 
 
 def conv_taps_prepare(w):
-    """Tap-major copy [kh*kw][co][ci] of a [co][ci][kh][kw] filter and its TF32 residual (once
-    per weight)."""
+    """Tap-major copy [kh*kw][co][ci] of a [co][ci][kh][kw] filter, split into its TF32 leading part
+    (rounded to nearest) and residual (once per weight)."""
     co, ci = w.shape[0], w.shape[1]
     taps = w.permute(2, 3, 0, 1).reshape(-1, co, ci).contiguous()
-    return taps, tf32_residual(taps)
+    return tf32_split(taps)
 
 
 conv3x3_prepare = conv_taps_prepare
@@ -687,7 +699,7 @@ def conv_im2col_prepare(w):
     k_pad = (k + 3) // 4 * 4
     w2 = torch.zeros((1, co, k_pad), dtype=torch.float32, device=w.device)
     w2[0, :, :k] = w.reshape(co, k)
-    return w2, tf32_residual(w2), k_pad
+    return tf32_split(w2) + (k_pad,)
 
 
 def conv_im2col_forward_x3(x, prepared, kernel, stride, pad, bias=None, out=None, scratch=None, out_relu=None):

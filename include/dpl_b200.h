@@ -241,6 +241,9 @@ int dpl_gemm_tf32(const float* d_a, int a_major, long long lda, long long a_batc
  * d_blob_min / d_blob_max / d_relu_min / d_relu_max (optional, one float each): fused range statistics of D
  * and of the Relu output, as in dpl_clip_f32 (same arguments on dpl_conv_taps_tf32x3). */
 int dpl_tf32_residual_f32(const float* d_x, float* d_lo, uint64_t n, void* stream);
+/* Unbiased split of a weight for the 3xTF32 kernels: d_hi = RN_tf32(x) (round to nearest instead of the
+ * truncation kind::tf32 applies to a raw fp32 pattern), d_lo = RN_tf32(x - d_hi). Pass d_hi as the weight. */
+int dpl_tf32_split_f32(const float* d_x, float* d_hi, float* d_lo, uint64_t n, void* stream);
 int dpl_gemm_tf32x3(const float* d_a, const float* d_a_lo, int a_major, long long lda,
                     long long a_batch_stride, const float* d_b, int b_major, long long ldb,
                     long long b_batch_stride, float* d_d, long long ldd, long long d_batch_stride,

@@ -9,6 +9,16 @@ torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 g = torch.Generator(device="cuda").manual_seed(5)
 print("DPL_X3_ALT =", os.environ.get("DPL_X3_ALT", "1"))
+RN = os.environ.get("X3_RN", "0") == "1"   # operands pre-rounded to TF32 (round to nearest): isolates the accumulation error
+
+
+def rn_tf32(t):
+    u = t.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    r = (u + 0xFFF + ((u >> 13) & 1)) & 0xFFFFE000
+    r = torch.where(r >= 2 ** 31, r - 2 ** 32, r)
+    return r.to(torch.int32).view(torch.float32)
+
+
 for (n, ci, co, hw, k, relu_in) in [(8, 2048, 512, 14, 1, True), (8, 1024, 256, 14, 1, True), (8, 256, 1024, 14, 1, True),
                                     (8, 512, 512, 7, 3, True), (8, 256, 256, 14, 3, True), (8, 64, 64, 56, 3, True),
                                     (8, 512, 512, 7, 3, False)]:
@@ -18,6 +28,8 @@ for (n, ci, co, hw, k, relu_in) in [(8, 2048, 512, 14, 1, True), (8, 1024, 256, 
     w = torch.randn((co, ci, k, k), device="cuda", generator=g) * 0.05
     if relu_in:
         w = w.abs()
+    if RN:
+        x, w = rn_tf32(x), rn_tf32(w)
     want = F.conv2d(x.double(), w.double(), None, padding=k // 2)
     ref32 = F.conv2d(x, w, None, padding=k // 2)
     if k == 1:
