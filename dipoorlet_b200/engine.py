@@ -496,7 +496,8 @@ class Engine:
                         and x.shape[1] % 4 == 0 and x.is_contiguous()):
                     try:
                         return [K.linear_forward_x3(x, w, None, c, out=self._new((x.shape[0], w.shape[0]), x),
-                                                    rng=self._rng(node.output[0]))]
+                                                    rng=self._rng(node.output[0]),
+                                                    split=self._split(node.input[1], w))]
                     except K.GemmUnsupported:
                         self._fallback(node)
                 return [F.linear(x, w, c)]

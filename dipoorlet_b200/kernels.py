@@ -575,14 +575,21 @@ def conv1x1_px_forward_x3(x, w, w_lo, bias=None, out=None, out_relu=None):
     return o
 
 
-def linear_forward_x3(x, w, w_lo=None, bias=None, out=None, rng=None):
-    """fp32-accurate Y = X W^T (+ bias): A = X (its residual is computed here, X is small),
-    B = W is split inside the kernel, so `w_lo` is not needed."""
+def linear_forward_x3(x, w, w_lo=None, bias=None, out=None, rng=None, split=None):
+    """fp32-accurate Y = X W^T (+ bias) on the tap-table kernel with ONE tap: the rows of X are the "pixels"
+    (TMEM lanes), W [out][k] is the tap's filter - so the Gemm layer gets the chunked accumulation and the
+    unbiased operand split of the convolutions (dpl_x3p.cuh). `split` = tf32_split(w) if the caller caches it."""
     nrow, k = x.shape
     out_f = w.shape[0]
     y = torch.empty((nrow, out_f), dtype=torch.float32, device=x.device) if out is None else out
-    return gemm_tf32x3(x, tf32_residual(x), 0, k, 0, w, 0, k, 0, y, out_f, 0, nrow, out_f, k, batch=1,
-                       bias=bias, bias_mode=2 if bias is not None else 0, rng=rng)
+    w_hi, w_lo2 = split if split is not None else tf32_split(w)
+    shifts = (ctypes.c_int * 1)(0)
+    st = lib().dpl_conv_taps_tf32x3(x.data_ptr(), nrow, w_hi.data_ptr(), w_lo2.data_ptr(), y.data_ptr(), nrow, k,
+                                    out_f, 1, 1, 1, 1, 0, 1, shifts, _lib._ptr(bias), 0, 0, *_rng(rng), 0, 0,
+                                    _err_flag(x.device).data_ptr(), _stream())
+    _unsupported(st, "dpl_conv_taps_tf32x3")
+    _count()
+    return y
 
 
 def conv_taps_prepare(w):
