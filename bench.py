@@ -487,9 +487,14 @@ def run_finetune(args):
                 e1.record()
                 record.append((names, epochs * n_batches, e0, e1, learning.TIMINGS[-1]))
             iters += epochs * n_batches
+            for l in ls:     # order-sensitive checksum of the learned rounding state (replica comparison)
+                bits = l.round_mask.view(torch.int32).to(torch.int64)
+                checksum[bi % 64] = (checksum[bi % 64] * 1000003 + bits.sum() + (bits * (1 + torch.arange(
+                    bits.numel(), device=dev).view(bits.shape) % 8191)).sum()) % (2 ** 61 - 1)
         return iters
 
     learning.TIMINGS = []
+    checksum = torch.zeros(64, dtype=torch.int64, device=dev)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -522,6 +527,12 @@ def run_finetune(args):
     ms = float(ms.item())
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     K.gemm_check_errors()
+    identical = None
+    if world > 1:    # DDP semantics: averaged gradients + identical updates keep the replicas bit-identical
+        hi, lo = checksum.clone(), checksum.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        identical = bool(torch.equal(hi, lo))
     if rank != 0:
         dist.destroy_process_group()
         return
@@ -547,7 +558,7 @@ def run_finetune(args):
                              "L2 resident as in the real job" % n_img,
                        "gradient_reduction": ("peer (NVLink, in the step kernel)" if os.environ.get(
                            "DPL_PEER_ALLREDUCE") == "1" else "NCCL all-reduce per layer") if world > 1 else "none"},
-            "clocks": clocks, "gpu_launches": launches, "per_block": per_block}
+            "clocks": clocks, "gpu_launches": launches, "replicas_bit_identical": identical, "per_block": per_block}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -918,4 +918,4 @@ def conv_im2col_wgrad(x, go, kernel, stride, pad, scratch=None):
     split = max(1, min(n, 296 // max(tiles, 1)))
     gemm_tf32(go, 0, px, co * px, scratch, 1, k_pad, px * k_pad, dw, k_pad, 0, co, k_pad, px, batch=n,
               fold_batch=True, split_k=split)
-    return dw[:, :k].reshape(co, c, kh, kw)
+    return dw[:, :k].reshape(co, c, kh, kw).contiguous()
