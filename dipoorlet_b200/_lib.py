@@ -95,7 +95,7 @@ SIGNATURES = {
     "dpl_im2col_f32": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                 _c_int, _c_int, _c_int, _c_vp]),
     "dpl_conv1x1_px_tf32x3": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp,
-                                       _c_vp, _c_vp]),
+                                       _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "dpl_clip_f32": (_c_int, [_c_vp, _c_vp, _c_u64, _c_flt, _c_flt, _c_vp, _c_vp, _c_vp]),
     "dpl_add_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_u64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "dpl_maxpool2d_f32": (_c_int, [_c_vp, _c_vp, _c_u64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,

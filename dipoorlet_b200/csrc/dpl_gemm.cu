@@ -1549,6 +1549,7 @@ int make_map_px(CUtensorMap* map, const float* base, uint64_t hw, uint64_t c_in,
 }
 
 #include "dpl_x3p.cuh"
+#include "dpl_x3ts.cuh"
 
 }  // namespace
 }  // namespace dpl
@@ -1863,6 +1864,14 @@ extern "C" int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, con
   p.bmax = d_blob_max;
   p.rmin = d_relu_min;
   p.rmax = d_relu_max;
+  if (!taps_ts && x3_chunk_iters() > 0 && x3_ts()) {
+    // persistent kernel, chunked accumulation, activations through TMEM (dpl_x3ts.cuh)
+    const long long total = ((q_total + kBM - 1) / kBM) * ((c_out + bn - 1) / bn);
+    int e = launch_x3ts<0>(tmX, tmW, tmWlo, p, total, static_cast<cudaStream_t>(stream));
+    if (e) return e;
+    DPL_LAUNCH_CHECK("x3ts_kernel<0>");
+    return 0;
+  }
   if (!taps_ts && x3_chunk_iters() > 0) {
     // persistent kernel with chunked accumulation (dpl_x3p.cuh)
     X3PParams xp;
@@ -1912,6 +1921,7 @@ extern "C" int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, con
 //   hw and c_in multiples of 4 (TMA strides), else DPL_E_UNSUPPORTED.
 extern "C" int dpl_conv1x1_px_tf32x3(const float* d_x, const float* d_w, const float* d_w_lo, float* d_y, int n_img,
                                      int c_in, int c_out, int hw, const float* d_bias, float* d_y_relu,
+                                     float* d_blob_min, float* d_blob_max, float* d_relu_min, float* d_relu_max,
                                      int* d_error_flag, void* stream) {
   DPL_REQUIRE(d_x && d_w && d_w_lo && d_y, "null pointer");
   DPL_REQUIRE(n_img > 0 && c_in > 0 && c_out > 0 && hw > 0, "empty problem");
@@ -1919,6 +1929,41 @@ extern "C" int dpl_conv1x1_px_tf32x3(const float* d_x, const float* d_w, const f
   CUtensorMap tmX, tmW, tmWlo;
   int st = make_map_px(&tmX, d_x, (uint64_t)hw, (uint64_t)c_in, (uint64_t)n_img);
   if (st) return st;
+  if (x3_chunk_iters() > 0 && x3_ts()) {
+    // persistent kernel, chunked accumulation (dpl_x3ts.cuh): 128 px x (64 | 128) co tiles
+    const int bn = c_out <= 64 ? 64 : 128;
+    st = make_map(&tmW, d_w, (uint64_t)c_in, (uint64_t)c_out, 1, (uint64_t)c_in, 0, (uint32_t)bn, false);
+    if (!st) st = make_map(&tmWlo, d_w_lo, (uint64_t)c_in, (uint64_t)c_out, 1, (uint64_t)c_in, 0, (uint32_t)bn, false);
+    if (st) return st;
+    ConvParams c = ConvParams();
+    c.n_img = n_img;
+    c.c_in = c_in;
+    c.c_out = c_out;
+    c.H = hw;
+    c.W = 1;
+    c.Wp = 1;
+    c.plane = hw;
+    c.origin = 0;
+    c.n_taps = 1;
+    c.bn = bn;
+    c.q_total = (long long)n_img * hw;
+    c.Y = d_y;
+    c.bias = d_bias;
+    c.relu = 0;
+    c.error_flag = d_error_flag;
+    c.Y2 = d_y_relu;
+    c.bmin = d_blob_min;
+    c.bmax = d_blob_max;
+    c.rmin = d_relu_min;
+    c.rmax = d_relu_max;
+    const long long total = (long long)((hw + kBM - 1) / kBM) * n_img * ((c_out + bn - 1) / bn);
+    int e = launch_x3ts<1>(tmX, tmW, tmWlo, c, total, static_cast<cudaStream_t>(stream));
+    if (e) return e;
+    DPL_LAUNCH_CHECK("x3ts_kernel<1>");
+    return 0;
+  }
+  DPL_REQUIRE(!d_blob_min && !d_blob_max && !d_relu_min && !d_relu_max,
+              "fused range statistics need the chunked kernel (DPL_X3_CHUNK > 0, DPL_X3_TS = 1)");
   st = make_map(&tmW, d_w, (uint64_t)c_in, (uint64_t)c_out, 1, (uint64_t)c_in, 0, (uint32_t)kPxBN, false);
   if (!st) st = make_map(&tmWlo, d_w_lo, (uint64_t)c_in, (uint64_t)c_out, 1, (uint64_t)c_in, 0, (uint32_t)kPxBN, false);
   if (st) return st;

@@ -63,9 +63,10 @@ class Engine:
         self.tc_conv3x3 = os.environ.get("DPL_ENGINE_CONV3X3", "1") != "0"
         self._tc_off = set()       # nodes the tensor-core tile could not address
         self.tensor_cores = os.environ.get("DPL_ENGINE_TCGEN05", "1") != "0"
-        # pixel-major TMEM-operand tile (dpl_conv1x1_px_tf32x3): correct and tested, but measured slower than
-        # the channel-major persistent tile on ResNet-50's shapes, so opt-in
-        self.conv1x1_px = os.environ.get("DPL_ENGINE_CONV1X1_PX", "0") == "1"
+        # 1x1 convolutions on the pixel-major tile with the activations through TMEM (dpl_conv1x1_px_tf32x3 ->
+        # csrc/dpl_x3ts.cuh) instead of the channel-major tile with both operands in shared memory
+        # (dpl_gemm_tf32x3 -> csrc/dpl_x3p.cuh); DPL_ENGINE_CONV1X1_PX=0 selects the latter
+        self.conv1x1_px = os.environ.get("DPL_ENGINE_CONV1X1_PX", "1") == "1"
         self.native_ops = os.environ.get("DPL_ENGINE_NATIVE_OPS", "1") != "0"
         # Relu blob written by the Conv epilogue (second store stream). Measured on B200, hist job: a loss
         # with the row-per-thread epilogue stores (convolutions 6.07 -> 6.66 ms per 64 images), a small gain
@@ -333,7 +334,9 @@ class Engine:
                     r = self._relu_out(node, out, env)
                     w_hi, w_lo = self._split(node.input[1], w2)
                     if self.conv1x1_px:
-                        y = K.conv1x1_px_forward_x3(x, w_hi, w_lo, b, out=out, out_relu=r)
+                        y = K.conv1x1_px_forward_x3(x, w_hi, w_lo, b, out=out, out_relu=r,
+                                                    rng=self._rng(node.output[0]),
+                                                    rng_relu=self._rng_relu(node) if r is not None else None)
                     else:
                         y = K.conv1x1_forward_x3(x, w_hi, w_lo, b, out=out, out_relu=r,
                                                  rng=self._rng(node.output[0]),

@@ -552,7 +552,7 @@ def conv1x1_forward_x3(x, w, w_lo, bias=None, relu=False, out=None, out_relu=Non
                        rng_relu=rng_relu)
 
 
-def conv1x1_px_forward_x3(x, w, w_lo, bias=None, out=None, out_relu=None):
+def conv1x1_px_forward_x3(x, w, w_lo, bias=None, out=None, out_relu=None, rng=None, rng_relu=None):
     """fp32-accurate 1x1 convolution, pixel-major tile (activations through TMEM), NCHW in / out."""
     _need(x, torch.float32, "x")
     _need(w, torch.float32, "w")
@@ -567,7 +567,8 @@ def conv1x1_px_forward_x3(x, w, w_lo, bias=None, out=None, out_relu=None):
     if flag is None:
         flag = _gemm_err[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
     st = lib().dpl_conv1x1_px_tf32x3(x.data_ptr(), w.data_ptr(), w_lo.data_ptr(), o.data_ptr(), n, ci, co,
-                                     hh * ww, _lib._ptr(bias), _lib._ptr(out_relu), flag.data_ptr(), _stream())
+                                     hh * ww, _lib._ptr(bias), _lib._ptr(out_relu), *_rng(rng), *_rng(rng_relu),
+                                     flag.data_ptr(), _stream())
     if st == 10003:
         raise GemmUnsupported(lib().dpl_last_error().decode("utf-8", "replace"))
     check(st, "dpl_conv1x1_px_tf32x3")

@@ -305,11 +305,14 @@ int dpl_im2col_f32(const float* d_x, float* d_xp, int n_img, int channels, int H
  *   Y[img][co][px] = bias[co] + sum_ci W[co][ci] * X[img][ci][px]
  * with the pixels on the TMEM lanes and the activations as the TMEM operand of tcgen05.mma (split
  * into TF32 pattern + residual in registers), weights + host residual by TMA; 128 px x 64 co tiles,
- * two CTAs per SM. d_y_relu (optional) also receives max(Y, 0). hw and c_in must be multiples of 4
+ * two CTAs per SM; by default (DPL_X3_CHUNK > 0, DPL_X3_TS = 1) the persistent kernel with chunked
+ * accumulation (128 px x 128 co tiles, csrc/dpl_x3ts.cuh), which also folds the fused range statistics
+ * d_blob_* / d_relu_* (see dpl_clip_f32). d_y_relu (optional) also receives max(Y, 0). hw and c_in must be multiples of 4
  * (TMA strides), otherwise DPL_E_UNSUPPORTED. Same reference operator as dpl_gemm_tf32x3
  * (the Conv nodes ORT executes in dipoorlet/forward_net.py:200-216). */
 int dpl_conv1x1_px_tf32x3(const float* d_x, const float* d_w, const float* d_w_lo, float* d_y, int n_img,
                           int c_in, int c_out, int hw, const float* d_bias, float* d_y_relu,
+                          float* d_blob_min, float* d_blob_max, float* d_relu_min, float* d_relu_max,
                           int* d_error_flag, void* stream);
 
 /* Non-GEMM operators of the calibration forward — the Relu / Clip / Add / MaxPool /
