@@ -1929,7 +1929,7 @@ extern "C" int dpl_conv1x1_px_tf32x3(const float* d_x, const float* d_w, const f
   CUtensorMap tmX, tmW, tmWlo;
   int st = make_map_px(&tmX, d_x, (uint64_t)hw, (uint64_t)c_in, (uint64_t)n_img);
   if (st) return st;
-  if (x3_chunk_iters() > 0 && x3_ts()) {
+  if (x3_chunk_iters() > 0) {
     // persistent kernel, chunked accumulation (dpl_x3ts.cuh): 128 px x (64 | 128) co tiles
     const int bn = c_out <= 64 ? 64 : 128;
     st = make_map(&tmW, d_w, (uint64_t)c_in, (uint64_t)c_out, 1, (uint64_t)c_in, 0, (uint32_t)bn, false);

@@ -65,8 +65,9 @@ class Engine:
         self.tensor_cores = os.environ.get("DPL_ENGINE_TCGEN05", "1") != "0"
         # 1x1 convolutions on the pixel-major tile with the activations through TMEM (dpl_conv1x1_px_tf32x3 ->
         # csrc/dpl_x3ts.cuh) instead of the channel-major tile with both operands in shared memory
-        # (dpl_gemm_tf32x3 -> csrc/dpl_x3p.cuh); DPL_ENGINE_CONV1X1_PX=0 selects the latter
-        self.conv1x1_px = os.environ.get("DPL_ENGINE_CONV1X1_PX", "1") == "1"
+        # (dpl_gemm_tf32x3 -> csrc/dpl_x3p.cuh): correct and tested, but measured slower on ResNet-50's
+        # shapes (hist job 5 660 vs 7 510 images/s, profiles/r2_summary.md), so opt-in
+        self.conv1x1_px = os.environ.get("DPL_ENGINE_CONV1X1_PX", "0") == "1"
         self.native_ops = os.environ.get("DPL_ENGINE_NATIVE_OPS", "1") != "0"
         # Relu blob written by the Conv epilogue (second store stream). Measured on B200, hist job: a loss
         # with the row-per-thread epilogue stores (convolutions 6.07 -> 6.66 ms per 64 images), a small gain
