@@ -610,7 +610,12 @@ class ConvPlan:
     def __init__(self, n, h, w, ksize, stride):
         self.n, self.h, self.w, self.stride = n, h, w, stride
         if ksize == 3 and stride == 1:
-            self.ho, self.wo, self.hp, self.wp, self.origin, self.planes = h, w, h + 2, w + 2, 1, 1
+            # compact zero border: ONE zero column per row and ONE zero row per image, shared with the next row /
+            # image (pixel (h, w) at h * (W + 1) + w; column W of row h is also column -1 of row h + 1, the zero
+            # row behind image i is also row -1 of image i + 1; rows before the first image are TMA's zero fill).
+            # (H + 1)(W + 1) plane points per image instead of (H + 2)(W + 2): 1.31 -> 1.15 x the useful work
+            # at 14 x 14, 1.65 -> 1.31 at 7 x 7.
+            self.ho, self.wo, self.hp, self.wp, self.origin, self.planes = h, w, h + 1, w + 1, 0, 1
             self.shifts = [(kh - 1) * self.wp + (kw - 1) for kh in range(3) for kw in range(3)]
         elif ksize == 3 and stride == 2:
             self.ho, self.wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
@@ -629,7 +634,7 @@ class ConvPlan:
 
 
 def conv3x3_plane_pitch(h, w):
-    return (h + 2) * (w + 2)
+    return (h + 1) * (w + 1)
 
 
 def conv_taps_forward_x3(x, taps, taps_lo, ksize, stride, bias=None, relu=False, out=None, scratch=None,
