@@ -30,6 +30,7 @@ constexpr int kX3PStageBytes = 4 * kTileBytes;                 // 64 KB
 constexpr int kX3PStgBytes = 4 * 32 * 36 * 4;                  // MODE 0 store staging, one 32 x 36 tile per warp
 
 struct X3PParams {
+  int single;           // 1: single-pass TF32 (leading term only, no residual tiles) - the reconstruction loop's numerics
   int chunk_iters;      // K blocks (of 32) accumulated in TMEM before a drain
   GemmParams g;         // MODE 0
   ConvParams c;         // MODE 1
@@ -132,19 +133,19 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
           const uint32_t t0 = tiles + s * kX3PStageBytes, t1 = t0 + kTileBytes, t2 = t0 + 2 * kTileBytes,
                          t3 = t0 + 3 * kTileBytes;
           if (MODE == 0) {
-            bar_expect_tx(full, 3 * kTileBytes);
+            bar_expect_tx(full, (p.single ? 2 : 3) * kTileBytes);
             const int k0 = i * kBK;
             tma_load_3d(t0, &tmW, k0, m0, 0, full);
-            tma_load_3d(t1, &tmWlo, k0, m0, 0, full);
+            if (!p.single) tma_load_3d(t1, &tmWlo, k0, m0, 0, full);
 #pragma unroll
             for (int j = 0; j < kBN / 32; ++j) tma_load_3d(t2 + j * (kBK * 128), &tmX, n0 + 32 * j, k0, z, full);
           } else {
-            bar_expect_tx(full, kTileBytes + 2u * (uint32_t)bn * 128u);
+            bar_expect_tx(full, kTileBytes + (p.single ? 1u : 2u) * (uint32_t)bn * 128u);
             const int kb = i / p.c.n_taps, tap = i - kb * p.c.n_taps;
             const int k0 = kb * kBK;
             tma_load_3d(t0, &tmX, k0, m0 + p.c.tap_shift[tap], 0, full);
             tma_load_3d(t2, &tmW, k0, n0, tap, full);
-            tma_load_3d(t3, &tmWlo, k0, n0, tap, full);
+            if (!p.single) tma_load_3d(t3, &tmWlo, k0, n0, tap, full);
           }
         }
       }
@@ -168,13 +169,31 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
           for (; i < cend; ++i, ++it) {
             const int s = it % kX3PStages;
             const uint32_t ph = (it / kX3PStages) & 1;
-            if (!bar_wait(smem_addr(&s_ready[s]), ph)) {
+            if (!bar_wait(smem_addr(p.single ? &s_full[s] : &s_ready[s]), ph)) {   // single: no transform step
               failed = true;
               break;
             }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t t0 = tiles + s * kX3PStageBytes, t1 = t0 + kTileBytes, t2 = t0 + 2 * kTileBytes,
                            t3 = t0 + 3 * kTileBytes;
+            if (p.single) {
+#pragma unroll
+              for (int j = 0; j < kBK / kUmmaK; ++j) {
+                const uint64_t da = desc_k_major(t0, j);
+                const uint64_t db = MODE == 0 ? desc_mn_major(t2, j) : desc_k_major(t2, j);
+                const uint32_t accumulate = (i > cbeg || j > 0) ? 1u : 0u;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "setp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                    ::"r"(acc_hi), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+                    : "memory");
+              }
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                               smem_addr(&s_empty[s]))
+                           : "memory");
+              continue;
+            }
 #pragma unroll
             for (int j = 0; j < kBK / kUmmaK; ++j) {
               uint64_t da, dal, db, dbl;
@@ -221,7 +240,7 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
     const int src_off = MODE == 0 ? 2 * kTileBytes : 0, dst_off = MODE == 0 ? 3 * kTileBytes : kTileBytes;
     int it = 0;
     bool failed = false;
-    for (int tile = blockIdx.x; tile < total_tiles && !failed && !s_fail; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total_tiles && !failed && !s_fail && !p.single; tile += gridDim.x) {
       for (int i = 0; i < iters; ++i, ++it) {
         const int s = it % kX3PStages;
         const uint32_t ph = (it / kX3PStages) & 1;
@@ -271,7 +290,12 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
           if (grp < n_grp) {
             uint32_t r[32], r2[32];
             tmem_ld32(lane_base + (uint32_t)(buf * 256 + grp * 32), r);
-            tmem_ld32(lane_base + (uint32_t)(buf * 256 + 128 + grp * 32), r2);
+            if (!p.single) {
+              tmem_ld32(lane_base + (uint32_t)(buf * 256 + 128 + grp * 32), r2);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r2[j] = 0u;
+            }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (c == 0) {
 #pragma unroll

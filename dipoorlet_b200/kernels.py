@@ -459,7 +459,9 @@ def conv1x1_dgrad(go, w, out=None):
     ci = w.shape[1]
     hw = hh * ww
     dx = torch.empty((n, ci, hh, ww), dtype=torch.float32, device=go.device) if out is None else out
-    return gemm_tf32(w, 1, ci, 0, go, 1, hw, co * hw, dx, hw, ci * hw, ci, hw, co, batch=n)
+    # W^T as a K-major operand (one tiny transposition): the K-major x MN-major form takes the persistent kernel
+    _, wt = taps_layout(w.reshape(co, ci, 1, 1), forward=False, dgrad=True)
+    return gemm_tf32(wt, 0, co, 0, go, 1, hw, co * hw, dx, hw, ci * hw, ci, hw, co, batch=n)
 
 
 def linear_forward(x, w, bias=None, relu=False):
