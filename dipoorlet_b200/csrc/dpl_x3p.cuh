@@ -17,17 +17,19 @@
 // boundaries, so a tile's epilogue (global stores) overlaps the next tile's main loop.
 //   warps 0-3   control: warp 0 / lane 0 TMA producer, warp 1 / lane 0 MMA issuer, warp 2 TMEM allocation
 //   warps 4-7   transform: lo tile of the activation operand, in shared memory (generic -> async proxy fence)
-//   warps 8-11  chunk drain + epilogue (TMEM lane quarter = warp - 8), 128 accumulator registers per thread;
-//               setmaxnreg moves registers from the other two warp groups to this one.
+//   warps 8-15  chunk drain + epilogue: TMEM lane quarter = warp % 4, warps 8-11 own the first half of the tile's
+//               columns and warps 12-15 the second (64 accumulator registers per thread; with four warps the
+//               epilogue of the short-K layers - 64 KB of stores per tile - was the bottleneck, 10 K clk per tile);
+//               setmaxnreg moves registers from the other two warp groups to these two.
 // MODE 0 (1x1 convolution / GEMM): D[z][m][n] = A[m][k] (weights, K-major, hi + lo by TMA) x B[z][k][n]
 //         (activations, MN-major: NCHW pixels contiguous), output channels on the TMEM lanes.
 // MODE 1 (tap-table convolution): D[q][co] = sum_tap Xp[q + shift(tap)][ci] (activations, K-major) x
 //         Wt[tap][co][ci] (weights, hi + lo by TMA), padded-plane pixels on the TMEM lanes (see ConvParams).
 
-constexpr int kX3PThreads = 384;
+constexpr int kX3PThreads = 512;
 constexpr int kX3PStages = 3;
 constexpr int kX3PStageBytes = 4 * kTileBytes;                 // 64 KB
-constexpr int kX3PStgBytes = 4 * 32 * 36 * 4;                  // MODE 0 store staging, one 32 x 36 tile per warp
+constexpr int kX3PStgBytes = 8 * 32 * 32 * 4;                  // MODE 0 store staging, one XOR-swizzled 32 x 32 tile per warp
 
 struct X3PParams {
   int single;           // 1: single-pass TF32 (leading term only, no residual tiles) - the reconstruction loop's numerics
@@ -88,7 +90,7 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
     }
     for (int b = 0; b < 2; ++b) {
       bar_init(smem_addr(&s_acc_full[b]), 1);
-      bar_init(smem_addr(&s_acc_empty[b]), 4);   // one arrival per drain warp
+      bar_init(smem_addr(&s_acc_empty[b]), 8);   // one arrival per drain warp
     }
     s_fail = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -264,18 +266,19 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
     }
     if (failed) s_fail = 1;
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
-    // ===== drain + epilogue warps (TMEM lane quarter = warp - 8) =====
-    const int wq = warp - 8;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;" ::: "memory");
+    // ===== drain + epilogue warps =====
+    const int wq = warp & 3, half = (warp - 8) >> 2;
     const uint32_t lane_base = tmem_acc + ((uint32_t)(wq * 32) << 16);
     const int n_chunks = (iters + chunk_iters - 1) / chunk_iters;
-    const int n_grp = bn / 32;
+    const int g_per = (bn / 32) / 2;          // column groups of 32 per warp: 2 (bn = 128) or 1 (bn = 64)
+    const int g_first = half * g_per;
     int g = 0;
     float rlo = INFINITY, rhi = -INFINITY;   // range of everything this thread stores, flushed once
-    float* stg = reinterpret_cast<float*>(tiles_ptr + kX3PStages * kX3PStageBytes) + wq * (32 * kStgPitch);
+    float* stg = reinterpret_cast<float*>(tiles_ptr + kX3PStages * kX3PStageBytes) + (warp - 8) * (32 * 32);
     bool failed = false;
     for (int tile = blockIdx.x; tile < total_tiles && !failed; tile += gridDim.x) {
-      float acc[128];
+      float acc[64];
       for (int c = 0; c < n_chunks; ++c, ++g) {
         const int buf = g & 1;
         bool ok = bar_wait(smem_addr(&s_acc_full[buf]), (g >> 1) & 1);
@@ -286,8 +289,9 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int grp = 0; grp < 4; ++grp) {
-          if (grp < n_grp) {
+        for (int gi = 0; gi < 2; ++gi) {
+          if (gi < g_per) {
+            const int grp = g_first + gi;
             uint32_t r[32], r2[32];
             tmem_ld32(lane_base + (uint32_t)(buf * 256 + grp * 32), r);
             if (!p.single) {
@@ -299,11 +303,11 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (c == 0) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) acc[grp * 32 + j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+              for (int j = 0; j < 32; ++j) acc[gi * 32 + j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                acc[grp * 32 + j] += __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+                acc[gi * 32 + j] += __uint_as_float(r[j]) + __uint_as_float(r2[j]);
             }
           }
         }
@@ -323,19 +327,19 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
         float* drow = q.D + (long long)z * q.d_batch_stride + (long long)m * q.ldd;
         const float bias_m = (q.bias_mode == 1 && m < q.M) ? q.bias[m] : 0.f;
 #pragma unroll
-        for (int grp = 0; grp < 4; ++grp) {
-          const int nc = n0 + grp * 32;
+        for (int gi = 0; gi < 2; ++gi) {
+          const int nc = n0 + (g_first + gi) * 32;
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            v[j] = acc[grp * 32 + j] + bias_m;
+            v[j] = acc[gi * 32 + j] + bias_m;
             if (q.relu) v[j] = fmaxf(v[j], 0.f);
             if (m < q.M && nc + j < q.N) {
               rlo = fminf(rlo, v[j]);
               rhi = fmaxf(rhi, v[j]);
             }
           }
-          // through a padded shared-memory tile: 4 rows x 128 contiguous bytes per store instruction
+          // through an XOR-swizzled shared-memory tile: 4 rows x 128 contiguous bytes per store instruction
           float* blk = q.D + (long long)z * q.d_batch_stride + (long long)(m0 + wq * 32) * q.ldd + nc;
           float* blk2 = q.D2 ? q.D2 + (blk - q.D) : nullptr;
           const bool fullblk = (m0 + wq * 32 + 32 <= q.M) && (nc + 32 <= q.N) && ((q.ldd & 3) == 0) &&
@@ -345,16 +349,17 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(stg + lane * kStgPitch + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              *reinterpret_cast<float4*>(stg + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) =
+                  make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             __syncwarp();
-            const int rr = lane >> 3, cc = (lane & 7) * 4;
+            const int rr = lane >> 3, c8 = lane & 7;
 #pragma unroll
             for (int qq = 0; qq < 8; ++qq) {
               const int row = 4 * qq + rr;
-              const float4 t = *reinterpret_cast<const float4*>(stg + row * kStgPitch + cc);
-              *reinterpret_cast<float4*>(blk + (long long)row * q.ldd + cc) = t;
+              const float4 t = *reinterpret_cast<const float4*>(stg + row * 32 + ((c8 ^ (row & 7)) << 2));
+              *reinterpret_cast<float4*>(blk + (long long)row * q.ldd + c8 * 4) = t;
               if (blk2)
-                *reinterpret_cast<float4*>(blk2 + (long long)row * q.ldd + cc) =
+                *reinterpret_cast<float4*>(blk2 + (long long)row * q.ldd + c8 * 4) =
                     make_float4(relu_keep_nan(t.x), relu_keep_nan(t.y), relu_keep_nan(t.z), relu_keep_nan(t.w));
             }
           } else if (m < q.M) {
@@ -386,14 +391,14 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
         const long long ch_stride = (long long)q.H * q.W;
         if (valid) {
 #pragma unroll
-          for (int grp = 0; grp < 4; ++grp) {
-            if (grp < n_grp) {
-              const int cb = co0 + grp * 32;
+          for (int gi = 0; gi < 2; ++gi) {
+            if (gi < g_per) {
+              const int cb = co0 + (g_first + gi) * 32;
               float* dst = q.Y + out_base + (long long)cb * ch_stride;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 if (cb + j < q.c_out) {
-                  float v = acc[grp * 32 + j];
+                  float v = acc[gi * 32 + j];
                   if (q.bias) v += __ldg(q.bias + cb + j);
                   if (q.relu) v = fmaxf(v, 0.f);
                   dst[(long long)j * ch_stride] = v;
