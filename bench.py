@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--workload", default="hist", choices=["hist", "finetune"],
                     help="hist = BASELINE.json configs[1] (the headline, default); finetune = the brecq + drop "
                          "rounding loop of configs[4] on ResNet-50's blocks (see run_finetune)")
+    ap.add_argument("--algo", default="hist", choices=["hist", "mse", "minmax"],
+                    help="calibrator of the hist workload's model / images (default hist = the headline; mse = "
+                         "BASELINE.json configs[2] without --bc, minmax = configs[0] on the GPU)")
     ap.add_argument("--ft-images", type=int, default=256, help="finetune: calibration images per GPU")
     ap.add_argument("--ft-epoch", type=int, default=2, help="finetune: --ada_epoch (the CLI default 5000 is days)")
     ap.add_argument("--ft-model", default="r50", choices=["r50", "mbv2"])
@@ -111,6 +114,16 @@ class ClockSampler:
             return None
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+def _ncu_traffic(bytes_per_launch):
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_hist_traffic_ncu.json")))
+        if bytes_per_launch > 0 and abs(d["algorithmic_bytes_per_launch"] - bytes_per_launch) <= 1e-3 * bytes_per_launch:
+            return float(d["dram_bytes_read"] + d["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
 
 
 def measured_peak():
@@ -182,16 +195,27 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "bounded_sample_images_per_step": total_n // args.steps},
+            # the same workload description as the ours arm; the CPU arm times a bounded sample of it per step
+            # (per-image cost is constant), described under cpu_baseline.sample
+            "config": {"workload": WORKLOAD, "images_per_gpu": IMAGES_PER_GPU},
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": min(procs, sample), "kind": "port",
                              "sample": f"{total_n // args.steps} images per step, {min(procs, sample)} "
-                                       "single-threaded workers (torch-CPU fp32 forward + NumPy statistics)"},
+                                       "single-threaded workers (torch-CPU fp32 forward + NumPy statistics; the "
+                                       "reference's own forward is ONNXRuntime, not installable here - see DESIGN.md)"},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------ ours
+def _metric(algo):
+    return METRIC if algo == "hist" else METRIC.replace("-A hist --bins 2048", "-A " + algo)
+
+
+def _workload(algo):
+    return WORKLOAD if algo == "hist" else WORKLOAD.replace("-A hist --bins 2048", "-A " + algo)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -249,6 +273,13 @@ def run_ours(args):
         return sess, clip
 
     job.engine = None
+    if args.algo != "hist":
+        # mse / minmax: the plugin call itself with the images resident in HBM (no K2 to time separately)
+        def job(source, timed_hist=False):  # noqa: F811
+            a = mk_args(source)
+            a.act_quant = args.algo
+            fwd._SESSIONS.clear()
+            return tensor_calibration(graph, a)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -297,7 +328,7 @@ def run_ours(args):
 
     def e2e_job():
         a = mk_args(host)
-        a.act_quant = "hist"
+        a.act_quant = args.algo
         fwd._SESSIONS.clear()
         act, weight = tensor_calibration(graph, a)   # host dict of np.float32 clip values
         d2h["n"] = 8 * len(act)
@@ -318,10 +349,10 @@ def run_ours(args):
         return
     elems_per_img = W.blob_elements(W.resnet50_blob_shapes())
     line = {
-        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "metric": _metric(args.algo), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "images_per_gpu": n_img, "forward_batch": args.batch,
+        "config": {"workload": _workload(args.algo), "images_per_gpu": n_img, "forward_batch": args.batch,
                    "l2": "inputs larger than L2: every timed kernel streams a %.1f GB batch of blobs "
                          "(126 MB L2)" % (4 * elems_per_img * args.batch / 1e9),
                    "forward": ("libdpl_b200 only: 1x1 / 3x3 / strided conv + Gemm on tcgen05 3xTF32 tiles (fp32-accurate), 7x7 stem "
@@ -338,11 +369,11 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "K2 dpl_hist_abs_f32 variant %d" % (args.hist_variant or 7), "achieved": achieved, "peak": peak,
                      "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured"
                      else "fallback 6.65 TB/s", "unit": "GB/s", "frac": achieved / peak if peak else None,
-                     # dram__bytes_read + dram__bytes_write of this kernel from one `ncu --set full` capture
-                     # (profiles/r1_hist_v7_batch32_ncu.md: 3.4125 GB for 3.4046 GB algorithmic), scaled
-                     # to this run's bytes per launch
-                     "traffic": (1.00232 * float(np.mean(hist_bytes))) if hist_bytes else None,
-                     "traffic_source": "ncu capture at batch 32, scaled by bytes per launch",
+                     # dram__bytes_read + dram__bytes_write of ONE launch of this kernel from an `ncu --set full`
+                     # capture of this very command (same batch, same blobs per launch), committed as
+                     # profiles/r2_hist_traffic_ncu.json; null when this run's bytes per launch differ from the capture's
+                     "traffic": _ncu_traffic(float(np.mean(hist_bytes)) if hist_bytes else 0.0),
+                     "traffic_source": "profiles/r2_hist_traffic_ncu.json (ncu --set full of this command, one launch)",
                      "launches_timed": len(hist_ms),
                      "bytes_per_launch": float(np.mean(hist_bytes)) if hist_bytes else 0,
                      "ms_per_launch": float(np.mean(hist_ms)) if hist_ms else None,
@@ -350,11 +381,14 @@ def run_ours(args):
                      "ms_per_launch_min": float(np.min(hist_ms)) if hist_ms else None,
                      "ms_per_launch_max": float(np.max(hist_ms)) if hist_ms else None},
     }
+    if args.algo != "hist":
+        line["roofline"] = None      # no separately timed kernel on these lines; see hbm_read_roofline
     # north_star: the job rate as a fraction of the HBM-read roofline of its two statistics passes
     # (2 x 4 B x elements per image at the measured peak); the forward that produces the blobs is extra
-    job_roof = peak * 1e9 / (2 * 4 * elems_per_img) * world
+    stat_passes = 2 if args.algo == "hist" else 1     # mse: the OCTAV re-reads are meant to hit L2
+    job_roof = peak * 1e9 / (stat_passes * 4 * elems_per_img) * world
     line["hbm_read_roofline"] = {"images_per_s": job_roof, "frac": value / job_roof,
-                                 "bytes_per_image": 2 * 4 * elems_per_img}
+                                 "bytes_per_image": stat_passes * 4 * elems_per_img}
     if not args.no_cpu_baseline and world == 1:
         try:
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
