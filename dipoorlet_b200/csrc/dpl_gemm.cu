@@ -811,6 +811,7 @@ struct ConvParams {
   int origin;           // 1: one-pixel top/left border in the padded plane, 0: none
   int n_taps;
   int tap_shift[9];     // row offset of every tap in Xp (plane base + window shift)
+  int tap_w[9];         // x3p MODE 1 only: weight slice of every tap (identity for the forward kernels)
   int bn;               // output channels per CTA (64 or 128)
   int hi_alt;           // alternate the leading term between two accumulators
   long long q_total;    // n_img * Pp
@@ -820,6 +821,7 @@ struct ConvParams {
   int* error_flag;
   float* Y2;            // optional second output max(Y, 0) (the Relu blob behind the Conv)
   float *bmin, *bmax, *rmin, *rmax;   // optional fused range statistics of Y / Y2
+  int os, oa, ob;       // x3p MODE 1 only: plane point (hq, wq) is output pixel (hq * os + oa, wq * os + ob); 1, 0, 0 = dense
 };
 
 __global__ void __launch_bounds__(kGemm3Threads, 1)
@@ -1586,6 +1588,65 @@ static int x3_persistent_max_k() {
   return v;
 }
 
+// Single-pass TF32 tap-table convolution on the persistent kernel (x3p MODE 1, single) for dpl_tap_conv_tf32
+// (dpl_recon_conv.cu): same arguments as its one-tile-per-CTA kernel. Opt-in (DPL_TAPCONV_PERSISTENT=1, returns < 0
+// otherwise): measured slower than the one-tile kernel with two CTAs per SM on every ResNet-50 shape (forward
+// 0.126 vs 0.112 ms at 64 ch / 56 x 56, 0.083 vs 0.061 at 256 ch / 14 x 14) - a single-pass MMA stream is short
+// enough that twice the TMA loads in flight matter more than the overlapped epilogue.
+namespace dpl {
+int tap_conv_tf32_persistent(const float* d_xp, long long total_rows, const float* d_w_taps, int n_w_taps, float* d_y,
+                             int n_img, int ck, int cn, int H, int W, int Hp, int Wp, int origin, int out_stride,
+                             int out_a, int out_b, int n_taps, const int* tap_shift, const int* tap_w,
+                             const float* d_bias, int* d_error_flag, cudaStream_t stream) {
+  static const bool on = [] {
+    const char* e = getenv("DPL_TAPCONV_PERSISTENT");
+    return e && e[0] == '1';
+  }();
+  if (!on) return -1;
+  const int bn = cn <= 64 ? 64 : 128;
+  CUtensorMap tmX, tmW;
+  int st = make_map(&tmX, d_xp, (uint64_t)ck, (uint64_t)total_rows, 1, (uint64_t)ck, 0, kBM, false);
+  if (!st)
+    st = make_map(&tmW, d_w_taps, (uint64_t)ck, (uint64_t)cn, (uint64_t)n_w_taps, (uint64_t)ck, (uint64_t)cn * ck,
+                  (uint32_t)bn, false);
+  if (st) return st;
+  X3PParams xp;
+  xp.single = 1;
+  xp.chunk_iters = 1 << 20;
+  xp.g = GemmParams();
+  ConvParams& c = xp.c;
+  c = ConvParams();
+  c.n_img = n_img;
+  c.c_in = ck;
+  c.c_out = cn;
+  c.H = H;
+  c.W = W;
+  c.Wp = Wp;
+  c.plane = Hp * Wp;
+  c.origin = origin;
+  c.n_taps = n_taps;
+  // the kernel loads the weight slice of iteration tap index t from slice t: gather the slices' indices into
+  // the shift table's order by passing tap_w through tap_shift's companion below
+  for (int t = 0; t < 9; ++t) c.tap_shift[t] = t < n_taps ? tap_shift[t] : 0;
+  for (int t = 0; t < 9; ++t) c.tap_w[t] = t < n_taps ? tap_w[t] : 0;
+  c.bn = bn;
+  c.hi_alt = 0;
+  c.q_total = (long long)n_img * c.plane;
+  c.Y = d_y;
+  c.bias = d_bias;
+  c.relu = 0;
+  c.error_flag = d_error_flag;
+  c.os = out_stride;
+  c.oa = out_a;
+  c.ob = out_b;
+  const long long total = ((c.q_total + kBM - 1) / kBM) * ((cn + bn - 1) / bn);
+  int e = launch_x3p<1>(tmW, tmW, tmX, xp, total, stream);
+  if (e) return e;
+  DPL_LAUNCH_CHECK("x3p_kernel<1> (single)");
+  return 0;
+}
+}  // namespace dpl
+
 // a_major / b_major: 0 = K-major (element (row, k) at row * ld + k), 1 = MN-major (at k * ld + row).
 extern "C" int dpl_gemm_tf32(const float* d_a, int a_major, long long lda, long long a_batch_stride,
                              const float* d_b, int b_major, long long ldb, long long b_batch_stride,
@@ -1879,6 +1940,7 @@ extern "C" int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, con
   p.origin = origin;
   p.n_taps = n_taps;
   for (int t = 0; t < 9; ++t) p.tap_shift[t] = t < n_taps ? tap_shift[t] : 0;
+  for (int t = 0; t < 9; ++t) p.tap_w[t] = t;
   p.bn = bn;
   p.hi_alt = x3_hi_alt();
   p.q_total = q_total;
@@ -1891,6 +1953,8 @@ extern "C" int dpl_conv_taps_tf32x3(const float* d_xp, long long total_rows, con
   p.bmax = d_blob_max;
   p.rmin = d_relu_min;
   p.rmax = d_relu_max;
+  p.os = 1;
+  p.oa = p.ob = 0;
   if (!taps_ts && x3_chunk_iters() > 0 && x3_ts()) {
     // persistent kernel, chunked accumulation, activations through TMEM (dpl_x3ts.cuh)
     const long long total = ((q_total + kBM - 1) / kBM) * ((c_out + bn - 1) / bn);
@@ -1984,6 +2048,7 @@ extern "C" int dpl_conv1x1_px_tf32x3(const float* d_x, const float* d_w, const f
     c.bmax = d_blob_max;
     c.rmin = d_relu_min;
     c.rmax = d_relu_max;
+    c.os = 1;
     const long long total = (long long)((hw + kBM - 1) / kBM) * n_img * ((c_out + bn - 1) / bn);
     int e = launch_x3ts<1>(tmX, tmW, tmWlo, c, total, static_cast<cudaStream_t>(stream));
     if (e) return e;

@@ -23,6 +23,11 @@
 #include "dpl_tc.cuh"
 
 namespace dpl {
+// dpl_gemm.cu: the persistent kernel of dpl_x3p.cuh in single-pass mode (overlapped epilogue on eight warps)
+int tap_conv_tf32_persistent(const float* d_xp, long long total_rows, const float* d_w_taps, int n_w_taps, float* d_y,
+                             int n_img, int ck, int cn, int H, int W, int Hp, int Wp, int origin, int out_stride,
+                             int out_a, int out_b, int n_taps, const int* tap_shift, const int* tap_w,
+                             const float* d_bias, int* d_error_flag, cudaStream_t stream);
 namespace {
 
 constexpr int kRcStages = 3;                    // 3 x 32 KB: two CTAs per SM (one's epilogue under the other's loop)
@@ -456,6 +461,12 @@ extern "C" int dpl_tap_conv_tf32(const float* d_xp, long long total_rows, const 
     return DPL_E_UNSUPPORTED;
   }
   for (int t = 0; t < n_taps; ++t) DPL_REQUIRE(tap_w[t] >= 0 && tap_w[t] < n_w_taps, "tap_w out of range");
+  {
+    const int st_p = tap_conv_tf32_persistent(d_xp, total_rows, d_w_taps, n_w_taps, d_y, n_img, ck, cn, H, W, Hp, Wp,
+                                              origin, out_stride, out_a, out_b, n_taps, tap_shift, tap_w, d_bias,
+                                              d_error_flag, static_cast<cudaStream_t>(stream));
+    if (st_p >= 0) return st_p;     // < 0: persistent path switched off, take the one-tile-per-CTA kernel below
+  }
   CUtensorMap tmX, tmW;
   int st = make_map(&tmX, d_xp, (uint64_t)ck, (uint64_t)total_rows, 1, (uint64_t)ck, 0, kBM, false);
   if (st) return st;

@@ -146,8 +146,8 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
             const int kb = i / p.c.n_taps, tap = i - kb * p.c.n_taps;
             const int k0 = kb * kBK;
             tma_load_3d(t0, &tmX, k0, m0 + p.c.tap_shift[tap], 0, full);
-            tma_load_3d(t2, &tmW, k0, n0, tap, full);
-            if (!p.single) tma_load_3d(t3, &tmWlo, k0, n0, tap, full);
+            tma_load_3d(t2, &tmW, k0, n0, p.c.tap_w[tap], full);
+            if (!p.single) tma_load_3d(t3, &tmWlo, k0, n0, p.c.tap_w[tap], full);
           }
         }
       }
@@ -384,8 +384,9 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
           const int img = (int)(pq / q.plane);
           const int r = (int)(pq - (long long)img * q.plane);
           const int hp = r / q.Wp, wp = r - hp * q.Wp;
-          const int ho = hp - q.origin, wo = wp - q.origin;
-          valid = ho >= 0 && ho < q.H && wo >= 0 && wo < q.W;
+          const int hq = hp - q.origin, wq2 = wp - q.origin;
+          const int ho = hq * q.os + q.oa, wo = wq2 * q.os + q.ob;
+          valid = hq >= 0 && wq2 >= 0 && ho < q.H && wo < q.W;
           out_base = (((long long)img * q.c_out) * q.H + ho) * q.W + wo;
         }
         const long long ch_stride = (long long)q.H * q.W;
