@@ -128,6 +128,8 @@ def _iteration(layers, x, t, reg_alpha, world, loss_acc, sched, seeds, peer=None
     schedule kernel), so the same launch sequence serves every iteration — eagerly or as a
     replayed CUDA graph."""
     last = len(layers) - 1
+    overlap = os.environ.get("DPL_OVERLAP_ALLREDUCE", "1") != "0"
+    pending = []
     acts, outs, cfgs = [x], [], []
     for li, layer in enumerate(layers):
         w = layer.quant_weight(soft=True)
@@ -151,6 +153,10 @@ def _iteration(layers, x, t, reg_alpha, world, loss_acc, sched, seeds, peer=None
             K.adaround_step_peer(grads, words, peer.rank, peer.epoch, layer.wfloor, layer.scale, layer.q_min,
                                  layer.q_max, 0.0, layer.round_mask, layer.m, layer.v, 1, reg_alpha=reg_alpha,
                                  sched=sched, error=peer.error)
+        elif world > 1 and overlap:
+            # SUM on NCCL's stream (the 1/world is folded into the step) while the earlier layers' backward runs on
+            # ours: the <= 2.4 MB reductions are latency bound, so hide them instead of waiting three times
+            pending.append((layer, gw, torch.distributed.all_reduce(gw, async_op=True)))
         else:
             if world > 1:
                 torch.distributed.all_reduce(gw)   # SUM; the 1/world is folded into the step
@@ -158,6 +164,10 @@ def _iteration(layers, x, t, reg_alpha, world, loss_acc, sched, seeds, peer=None
                             layer.m, layer.v, 1, reg_alpha=reg_alpha, grad_scale=1.0 / world, sched=sched)
         if li > 0:
             go = K.recon_act_bwd(outs[li - 1], gx, **cfgs[li - 1])
+    for layer, gw, work in pending:
+        work.wait()                                # our stream waits for NCCL's, the host does not block
+        K.adaround_step(gw, layer.wfloor, layer.scale, layer.q_min, layer.q_max, 0.0, layer.round_mask,
+                        layer.m, layer.v, 1, reg_alpha=reg_alpha, grad_scale=1.0 / world, sched=sched)
 
 
 def _learn(layers, q_in, tgt, reg, batch_size, max_epoch, fp_in, drop, log_every, head, seed):
