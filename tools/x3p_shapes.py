@@ -33,7 +33,7 @@ for ci, co, hw, k, st in shapes:
         taps, taps_lo = K.conv_taps_prepare(w)
         scratch = torch.empty(K.ReconConvPlan(B, hw, hw, k, st, k // 2).total_rows * ci, device="cuda")
         fn = lambda: K.conv_taps_forward_x3(x, taps, taps_lo, k, st, b, out=y, scratch=scratch, out_relu=y2)  # noqa: E731
-    for _ in range(2):
+    for _ in range(int(os.environ.get("WARMUP", "2"))):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
