@@ -320,6 +320,11 @@ class Engine:
 
     def _exec(self, node, env):
         op, a = node.op_type, node.attrs
+        if op in ("Conv", "ConvTranspose", "MaxPool", "AveragePool") and a.get("auto_pad", "NOTSET") not in ("NOTSET", "", None):
+            # graph.py's shape inference honours auto_pad; executing from `pads` alone would silently compute a
+            # differently padded layer into buffers sized for SAME / VALID
+            raise NotImplementedError("%s %s: auto_pad=%s is not supported by the engine (export with explicit pads)"
+                                      % (op, node.name, a.get("auto_pad")))
         x = self._val(node.input[0], env) if node.input and node.input[0] else None
         if op == "Conv":
             w = self._val(node.input[1], env)

@@ -191,7 +191,14 @@ def simplify(model):
                 b0 = (g.initializers[conv.input[2]].astype(np.float64)
                       if len(conv.input) > 2 and conv.input[2] else np.zeros_like(mean))
                 g.initializers[conv.input[1]] = (w * f.reshape(-1, *[1] * (w.ndim - 1))).astype(np.float32)
-                bname = conv.input[2] if len(conv.input) > 2 and conv.input[2] else conv.name + "_bias"
+                if len(conv.input) > 2 and conv.input[2]:
+                    bname = conv.input[2]
+                else:
+                    # nodes may still be unnamed here (names are assigned after simplification): derive the new
+                    # initializer's name from the Conv's output tensor, which is unique
+                    bname = n.input[0] + "_bias"
+                    while bname in g.initializers:
+                        bname += "_"
                 g.initializers[bname] = ((b0 - mean) * f + bias).astype(np.float32)
                 if len(conv.input) > 2:
                     conv.input[2] = bname

@@ -47,7 +47,7 @@ def quantize_profiling_multipass(graph_after_wt, graph_ori, act_clip_val, weight
     fp_eng = Engine(graph_ori, dev, _unit_test_cpu=dev.type != "cuda")
     q_eng = Engine(graph_q, dev, _unit_test_cpu=dev.type != "cuda")
     per = math.ceil(args.data_num / world)                      # profiling.py:48-51 (ceil rule)
-    st, ed = rank * per, min(rank * per + per, args.data_num)
+    st, ed = min(rank * per, args.data_num), min(rank * per + per, args.data_num)
     source = as_input_source(args.input_dir)
     in_shapes = {n: _per_image_shape(graph_ori, n) for n in graph_ori.network_inputs}
     layer_names = [t for node in quant_node_list for t in node.output]
@@ -86,7 +86,7 @@ def quantize_profiling_multipass(graph_after_wt, graph_ori, act_clip_val, weight
                 for j in range(host.shape[0]):
                     host[j].tofile(os.path.join(save_path, 'onnx-output-{}.bin'.format(b0 + j)))
         del fp, q
-    n_local = torch.tensor([float(ed - st)], dtype=torch.float64, device=dev)
+    n_local = torch.tensor([float(max(ed - st, 0))], dtype=torch.float64, device=dev)   # an empty ceil-rule shard counts 0
     if dist_helper.is_dist():
         for t in (layer_sum, out_sum, single_sums, n_local):
             dist_helper.allreduce_sum(t)

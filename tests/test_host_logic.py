@@ -495,3 +495,102 @@ def test_two_input_model_calibrates_in_reference_order(monkeypatch, tmp_path):
     ref = O.clip_hist(mm, O.hist_stats(blobs, mm, 2048), 2048, args.threshold)
     for k in ref:
         assert np.allclose(act[k], ref[k], rtol=2e-6, atol=1e-7), (k, act[k], ref[k])
+
+
+def test_bn_fold_of_unnamed_biasless_convs_keeps_biases_apart():
+    """simplify() runs before node names are assigned: two unnamed, bias-less Conv + BatchNormalization pairs must
+    not share one folded-bias initializer (round-1 advisor finding: both ended up reading `_bias`)."""
+    from dipoorlet_b200 import onnx_lite as ol
+    from dipoorlet_b200.graph import simplify
+    rng = np.random.default_rng(0)
+    g = ol.Graph()
+    g.inputs = [ol.ValueInfo("x", shape=[1, 3, 8, 8])]
+    g.outputs = [ol.ValueInfo("y", shape=[1, 5, 8, 8])]
+    chans = [(3, 4), (4, 5)]
+    prev = "x"
+    for i, (ci, co) in enumerate(chans):
+        g.initializers[f"w{i}"] = rng.standard_normal((co, ci, 1, 1)).astype(np.float32)
+        for k, v in (("s", 1.0), ("b", 0.5 + i), ("m", 0.1), ("v", 1.0)):
+            g.initializers[f"bn{i}_{k}"] = np.full(co, v, dtype=np.float32)
+        out = "y" if i == len(chans) - 1 else f"t{i}"
+        g.nodes.append(ol.Node("Conv", [prev, f"w{i}"], [f"c{i}"], name="", attrs=dict(kernel_shape=[1, 1])))
+        g.nodes.append(ol.Node("BatchNormalization", [f"c{i}", f"bn{i}_s", f"bn{i}_b", f"bn{i}_m", f"bn{i}_v"], [out],
+                               name="", attrs=dict(epsilon=1e-5)))
+        prev = out
+    m = simplify(ol.Model(g))
+    convs = [n for n in m.graph.nodes if n.op_type == "Conv"]
+    assert len(convs) == 2 and all(len(n.input) == 3 for n in convs)
+    assert convs[0].input[2] != convs[1].input[2]
+    b0, b1 = (m.graph.initializers[n.input[2]] for n in convs)
+    assert b0.shape == (4,) and b1.shape == (5,)
+    assert np.allclose(b0, (0.5 - 0.1) / np.sqrt(1 + 1e-5) * 1 + 0 * b0 + 0.0, atol=1e-5) or np.allclose(
+        b0, (0.0 - 0.1) / np.sqrt(1.0 + 1e-5) + 0.5, atol=1e-5)
+    assert np.allclose(b1, (0.0 - 0.1) / np.sqrt(1.0 + 1e-5) + 1.5, atol=1e-5)
+
+
+@pytest.mark.parametrize("algo", ["adaround", "brecq"])
+def test_learned_rounding_skips_equalised_layers_under_we(algo, monkeypatch, tmp_path):
+    """--we --adaround / --brecq: a layer whose weights were equalised cannot be mimicked against graph_ori's fp
+    output (adaround.py:35-36) and cannot close a brecq block (brecq.py:38-41). Host logic only: the learnable
+    layer, the activation caches and the optimisation loop are stand-ins that record what would be learned."""
+    import torch
+    from dipoorlet_b200 import onnx_lite as ol
+    from dipoorlet_b200.cli_args import make_args
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.weight_transform import adaround as A, brecq as B
+    from dipoorlet_b200.weight_transform.utils import LEARNABLE_LAYER_TYPES
+    from dipoorlet_b200.weight_transform.weight_equalization import node_has_equalized
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_r50")
+    model = ol.load(os.path.join(gold_dir, "model.onnx"))
+    calib = json.load(open(os.path.join(gold_dir, "calibration.json")))
+    gold_w = np.load(os.path.join(gold_dir, "weight_clip.npz"))
+    act = {k: [np.float64(v[0]), np.float64(v[1])] for k, v in calib["minmax"]["act"].items()}
+    weight = {}
+    for key in gold_w.files:
+        name, i = key.rsplit("|", 1)
+        weight.setdefault(name, [None, None])[int(i)] = gold_w[key].astype(np.float64)
+    graph = ONNXGraph(model, str(tmp_path), "trt")
+    learned = []
+
+    class Cache:
+        def __init__(self, *a, **k):
+            pass
+
+        def __getitem__(self, name):
+            return torch.zeros(1)
+
+        def update_initializers(self, *a, **k):
+            pass
+
+        def drop(self, *a, **k):
+            pass
+
+    class Layer:
+        def __init__(self, node, weight, *a, **k):
+            self.node, self.w = node, torch.as_tensor(weight)
+            learned.append(node.name)
+
+        def hard_weight(self):
+            return self.w
+
+    mod = A if algo == "adaround" else B
+    monkeypatch.setattr(mod, "ActivationCache", Cache)
+    monkeypatch.setattr(mod, "AdaQLayer", Layer)
+    blocks = []
+    monkeypatch.setattr(mod, "learning_round_mask", lambda layers, *a, **k: blocks.append([l.node.name for l in layers]))
+    args = make_args(input_dir=str(tmp_path), data_num=4, deploy="trt", act_quant="minmax", output_dir=str(tmp_path),
+                     ada_bs=2, ada_epoch=1, we=True, acti_quant=False, drop=False, **{algo: True})
+    getattr(mod, algo)(graph, graph, act, weight, args)
+    learnable = [n for n in graph.graph.node if n.op_type in LEARNABLE_LAYER_TYPES]
+    equalised = {n.name for n in learnable if node_has_equalized(graph, n)}
+    assert equalised and learned
+    if algo == "adaround":
+        assert set(learned) == {n.name for n in learnable} - equalised
+    else:
+        # an equalised layer may sit inside a block, but never at its end (here: conv1 / conv2 of a bottleneck are
+        # equalised, conv3 feeds the Add and is not, so every block survives whole)
+        assert blocks and all(b and b[-1] not in equalised for b in blocks)
+    learned.clear()
+    args.we = False
+    getattr(mod, algo)(graph, graph, act, weight, args)
+    assert set(learned) == {n.name for n in learnable}
