@@ -6,14 +6,14 @@ Replaces the reference's per-sample `ort.InferenceSession.run` with every node o
 promoted to a graph output and copied back to the host (dipoorlet/forward_net.py:195-216)
 and the per-node sessions of ActivationCache.forward_subnet (forward_net.py:81-128).
 
-1x1 / 3x3 / strided convolutions and Gemm layers run on libdpl_b200's tcgen05 tiles in 3xTF32 mode
-(fp32-accurate products on the TF32 tensor cores); the few-channel stem convolution on a direct fp32
-kernel (dpl_conv_direct.cu); Relu / Clip / Add (+ the Relu behind it) / MaxPool / GlobalAveragePool
-are libdpl_b200 streaming kernels (dpl_eltwise.cu) — a ResNet-50 forward issues no library kernel.
-STAND-IN NOTICE: what these do not cover yet (depthwise / grouped
-convolutions of MobileNetV2, rarely used operators) is still issued through torch's CUDA ops (cuDNN,
-true fp32: TF32 disabled), i.e. a library call playing the role onnxruntime's CUDA EP plays in the
-reference. QuantizeLinear + DequantizeLinear pairs are ONE fused K5 launch.
+1x1 / 3x3 / strided convolutions and Gemm layers run on libdpl_b200's tcgen05 tiles in 3xTF32 mode with chunked
+accumulation (fp32-accurate products on the TF32 tensor cores, csrc/dpl_x3p.cuh); the few-channel stem
+convolution and the depthwise convolutions of MobileNetV2 on exact-fp32 FMA kernels (dpl_conv_direct.cu);
+Relu / Clip / Add (+ the Relu behind it) / MaxPool / GlobalAveragePool are libdpl_b200 streaming kernels
+(dpl_eltwise.cu) - a ResNet-50 or MobileNetV2 forward issues no library kernel. Operators neither family
+contains (ConvTranspose, grouped non-depthwise or dilated convolutions, rarely used element-wise ops) are still
+issued through torch's CUDA ops (cuDNN with TF32 disabled), i.e. a library call playing the role onnxruntime's
+CUDA EP plays in the reference. QuantizeLinear + DequantizeLinear pairs are ONE fused K5 launch.
 
 Blob memory: when `engine.arena` is set (forward_net.CalibrationSession does) every node output is
 bump-allocated from that one slab instead of torch's caching allocator.

@@ -103,9 +103,10 @@ def learning_round_mask(layers, q_in, tgt, reg, batch_size, max_epoch, fp_in=Non
     trailing Relu when there is one), all float32 CUDA tensors [n, ...] resident in HBM.
     Returns the last mini-batch loss (as the reference logs it)."""
     # Numerics of the re-evaluation: the reference's F.conv2d runs with torch's default
-    # cudnn.allow_tf32 = True and F.linear in true fp32 (SURVEY.md A-8). Same here: TF32 tensor
-    # cores for the convolutions (tcgen05 tile for 1x1, cuDNN for the rest), fp32 for Gemm on
-    # the library path. DPL_RECON_TF32=0 forces fp32 everywhere (and the tcgen05 tile off).
+    # cudnn.allow_tf32 = True and F.linear in true fp32 (SURVEY.md A-8). Here every convolution and the Gemm
+    # layers run on libdpl_b200's single-pass TF32 tcgen05 kernels (depthwise / stem forward: exact fp32);
+    # DPL_RECON_TF32=0 switches those kernels off and forces true fp32 on the library path (torch / cuDNN) -
+    # a debugging aid for the update rule, used by tests/test_gpu_quant_kernels.py.
     tf32 = os.environ.get("DPL_RECON_TF32", "1") != "0"
     saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, os.environ.get("DPL_TCGEN05"))
     torch.backends.cudnn.allow_tf32 = tf32
