@@ -32,6 +32,7 @@ constexpr int kX3PStageBytes = 4 * kTileBytes;                 // 64 KB
 constexpr int kX3PStgBytes = 8 * 32 * 32 * 4;                  // MODE 0 store staging, one XOR-swizzled 32 x 32 tile per warp
 
 struct X3PParams {
+  int probe_skip_wlo;   // timing probe only (DPL_X3_PROBE_SKIP_WLO=1): do not load the W_lo tiles - WRONG results
   int single;           // 1: single-pass TF32 (leading term only, no residual tiles) - the reconstruction loop's numerics
   int chunk_iters;      // K blocks (of 32) accumulated in TMEM before a drain
   GemmParams g;         // MODE 0
@@ -135,19 +136,19 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
           const uint32_t t0 = tiles + s * kX3PStageBytes, t1 = t0 + kTileBytes, t2 = t0 + 2 * kTileBytes,
                          t3 = t0 + 3 * kTileBytes;
           if (MODE == 0) {
-            bar_expect_tx(full, (p.single ? 2 : 3) * kTileBytes);
+            bar_expect_tx(full, ((p.single || p.probe_skip_wlo) ? 2 : 3) * kTileBytes);
             const int k0 = i * kBK;
             tma_load_3d(t0, &tmW, k0, m0, 0, full);
-            if (!p.single) tma_load_3d(t1, &tmWlo, k0, m0, 0, full);
+            if (!p.single && !p.probe_skip_wlo) tma_load_3d(t1, &tmWlo, k0, m0, 0, full);
 #pragma unroll
             for (int j = 0; j < kBN / 32; ++j) tma_load_3d(t2 + j * (kBK * 128), &tmX, n0 + 32 * j, k0, z, full);
           } else {
-            bar_expect_tx(full, kTileBytes + (p.single ? 1u : 2u) * (uint32_t)bn * 128u);
+            bar_expect_tx(full, kTileBytes + ((p.single || p.probe_skip_wlo) ? 1u : 2u) * (uint32_t)bn * 128u);
             const int kb = i / p.c.n_taps, tap = i - kb * p.c.n_taps;
             const int k0 = kb * kBK;
             tma_load_3d(t0, &tmX, k0, m0 + p.c.tap_shift[tap], 0, full);
             tma_load_3d(t2, &tmW, k0, n0, p.c.tap_w[tap], full);
-            if (!p.single) tma_load_3d(t3, &tmWlo, k0, n0, p.c.tap_w[tap], full);
+            if (!p.single && !p.probe_skip_wlo) tma_load_3d(t3, &tmWlo, k0, n0, p.c.tap_w[tap], full);
           }
         }
       }
@@ -442,8 +443,14 @@ inline int x3_chunk_iters() {
 }
 
 template <int MODE>
-int launch_x3p(const CUtensorMap& tmW, const CUtensorMap& tmWlo, const CUtensorMap& tmX, const X3PParams& p,
+int launch_x3p(const CUtensorMap& tmW, const CUtensorMap& tmWlo, const CUtensorMap& tmX, const X3PParams& p_in,
                long long total_tiles, cudaStream_t s) {
+  static const int probe = [] {
+    const char* e = getenv("DPL_X3_PROBE_SKIP_WLO");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  X3PParams p = p_in;
+  p.probe_skip_wlo = probe;
   const size_t smem = (size_t)kX3PStages * kX3PStageBytes + kX3PStgBytes + 1024;
   static bool attr_done = false;
   if (!attr_done) {

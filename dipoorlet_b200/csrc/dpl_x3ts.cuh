@@ -331,8 +331,8 @@ x3ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
 }
 
 // Activations through TMEM for the tap-table convolutions: DPL_X3_TS=1 (opt-in; measured equal to slightly
-// slower than dpl_x3p.cuh on ResNet-50's 3x3 layers - the kernels are bound by L2 -> shared-memory traffic,
-// which is the same 48 KB per K block in both). dpl_conv1x1_px_tf32x3 always takes this kernel.
+// slower than dpl_x3p.cuh on ResNet-50's 3x3 layers: with one transform warp per scheduler the read - split -
+// tcgen05.st - handshake chain of a K block is longer than its MMAs). dpl_conv1x1_px_tf32x3 always takes this kernel.
 inline int x3_ts() {
   static int v = -1;
   if (v < 0) {
