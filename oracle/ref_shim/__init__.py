@@ -163,19 +163,28 @@ def _numpy_helper():
     return m
 
 
-def from_lite(model):
-    """dipoorlet_b200.onnx_lite.Model -> shim ModelProto (value_info filled by analytic
-    shape inference, standing in for what onnxsim leaves in the file)."""
-    from dipoorlet_b200.graph import ONNXGraph as LiteGraph
-    lg = LiteGraph(copy.deepcopy(model), "", None)
+def executed_shapes(model):
+    """name -> shape of every node output, read off the tensors the oracle's own forward (oracle/forward.py, torch-CPU
+    ops) produces for an all-zero input - independent of the product's analytic shape inference."""
+    from oracle import forward as OF
     g = model.graph
+    feeds = {v.name: np.zeros([int(d) for d in v.shape], dtype=np.float32) for v in g.inputs
+             if v.name not in g.initializers}
+    return {k: list(v.shape) for k, v in OF.forward_all(model, feeds).items()}
+
+
+def from_lite(model):
+    """dipoorlet_b200.onnx_lite.Model -> shim ModelProto. value_info (what onnxsim leaves in the file) is filled
+    from the shapes of an executed forward, NOT from dipoorlet_b200.graph's shape inference, so that the
+    graph-IR comparison against the reference can catch a shape-inference bug of the product."""
+    g = model.graph
+    shapes = executed_shapes(model)
     nodes = [NodeProto(n.op_type, n.input, n.output, n.name, dict(n.attrs)) for n in g.nodes]
     inits = [TensorProto(k, v.copy()) for k, v in g.initializers.items()]
     inputs = [ValueInfoProto(v.name, v.elem_type, v.shape) for v in g.inputs]
     outputs = [ValueInfoProto(v.name, v.elem_type, v.shape) for v in g.outputs]
     out_names = {v.name for v in g.outputs}
-    vinfo = [ValueInfoProto(o, 1, lg.get_tensor_shape(o)) for n in g.nodes for o in n.output
-             if o not in out_names]
+    vinfo = [ValueInfoProto(o, 1, shapes[o]) for n in g.nodes for o in n.output if o not in out_names]
     return ModelProto(GraphProto(nodes, g.name, inputs, outputs, inits, vinfo),
                       [_Opset(v, k) for k, v in model.opsets.items()])
 

@@ -594,3 +594,22 @@ def test_learned_rounding_skips_equalised_layers_under_we(algo, monkeypatch, tmp
     args.we = False
     getattr(mod, algo)(graph, graph, act, weight, args)
     assert set(learned) == {n.name for n in learnable}
+
+
+@pytest.mark.parametrize("builder", ["tiny_r50", "tiny_mbv2", "r50", "mbv2"])
+def test_shape_inference_equals_executed_shapes(builder):
+    """The product's analytic shape inference (graph.get_tensor_shape: arena sizing, quant-parameter shapes) against
+    the shapes of the tensors the oracle's forward actually produces (independent code: torch-CPU ops)."""
+    from dipoorlet_b200 import onnx_lite as ol
+    from dipoorlet_b200 import workloads as W
+    from dipoorlet_b200.graph import ONNXGraph
+    from oracle.ref_shim import executed_shapes
+    if builder.startswith("tiny"):
+        model = ol.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", builder, "model.onnx"))
+    else:
+        model = W.build_resnet50(seed=0, image=64) if builder == "r50" else W.build_mobilenetv2(seed=0, image=64)
+    graph = ONNXGraph(model, "", "trt")
+    want = executed_shapes(graph.model)
+    assert len(want) >= 20
+    for name, shape in want.items():
+        assert list(graph.get_tensor_shape(name)) == shape, name
