@@ -6,10 +6,9 @@
 // 3x3 / 512-channel convolution on same-sign data). One such layer is harmless, but ResNet-50 stacks 53 of them
 // and the shrink compounds: the calibration forward drifted 1e-6 per layer, 5e-5 at the last blob, against the
 // reference's fp32 CPU forward (tests/test_gpu_fullsize_parity.py) - beyond the 1e-5 the clip file is compared at.
-// Here the tensor core only ever accumulates `chunk_iters` K blocks (default 2 = 8 K steps) of LEADING terms in
-// TMEM; eight dedicated warps drain every chunk into REGISTER accumulators with round-to-nearest fp32 adds while
-// the MMA thread fills the next of three TMEM buffers. The cross terms are 2^-11 of the leading term: they keep
-// one accumulator for the whole tile and are added once at its end. The operand split is made unbiased as well: the weights' leading
+// Here the tensor core only ever accumulates `chunk_iters` K blocks (default 2 = 8 K steps) in TMEM; four
+// dedicated epilogue warps drain every chunk into REGISTER accumulators with round-to-nearest fp32 adds while
+// the MMA thread fills the other TMEM buffer. The operand split is made unbiased as well: the weights' leading
 // part is rounded to nearest on the host (w_hi = RN_tf32(w), w_lo = RN_tf32(w - w_hi)); the activations keep
 // the truncated fp32 pattern as their leading part (that is what kind::tf32 reads) and the transform warps
 // round the residual x - trunc(x) to TF32 to nearest, so the tensor core's own truncation of it is exact.
@@ -30,8 +29,6 @@
 constexpr int kX3PThreads = 512;
 constexpr int kX3PStages = 3;
 constexpr int kX3PStageBytes = 4 * kTileBytes;                 // 64 KB
-constexpr int kX3PHiBufs = 3;                                  // TMEM: three leading-term accumulators (columns 0 / 128 / 256) ...
-constexpr uint32_t kX3PLoCol = 384;                            // ... and ONE cross-term accumulator that runs over the whole tile
 constexpr int kX3PStgBytes = 8 * 32 * 32 * 4;                  // MODE 0 store staging, one XOR-swizzled 32 x 32 tile per warp
 
 struct X3PParams {
@@ -57,8 +54,8 @@ __global__ void __launch_bounds__(kX3PThreads, 1)
 x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
            const __grid_constant__ CUtensorMap tmX, const X3PParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_full[kX3PStages], s_ready[kX3PStages], s_empty[kX3PStages], s_acc_full[kX3PHiBufs],
-      s_acc_empty[kX3PHiBufs], s_lo_empty;
+  __shared__ __align__(8) uint64_t s_full[kX3PStages], s_ready[kX3PStages], s_empty[kX3PStages], s_acc_full[2],
+      s_acc_empty[2];
   __shared__ uint32_t s_tmem_base;
   __shared__ int s_fail;
 
@@ -92,11 +89,10 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
       bar_init(smem_addr(&s_ready[s]), 4);     // one arrival per transform warp
       bar_init(smem_addr(&s_empty[s]), 1);
     }
-    for (int b = 0; b < kX3PHiBufs; ++b) {
+    for (int b = 0; b < 2; ++b) {
       bar_init(smem_addr(&s_acc_full[b]), 1);
       bar_init(smem_addr(&s_acc_empty[b]), 8);   // one arrival per drain warp
     }
-    bar_init(smem_addr(&s_lo_empty), 8);
     s_fail = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -157,25 +153,20 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
         }
       }
     } else if (warp == 1 && lane == 0) {
-      // ===== MMA issuer =====
-      // Leading terms (hi x hi): chunks of chunk_iters K blocks go round robin through three TMEM accumulators that
-      // the drain warps empty into registers. Cross terms (lo x hi + hi x lo): ONE accumulator for the whole tile -
-      // they are 2^-11 of the leading term, so the truncation of their accumulation is negligible and they need no
-      // chunking: half the drain work per chunk, and the freed TMEM columns buy the third leading buffer.
+      // ===== MMA issuer: chunks of chunk_iters K blocks alternate between the two TMEM buffers =====
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((MODE == 0 ? 1u : 0u) << 16) |
                              ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-      const uint32_t acc_lo = tmem_acc + kX3PLoCol;
-      int it = 0, g = 0, t = 0;
+      int it = 0, g = 0;
       bool failed = false;
-      for (int tile = blockIdx.x; tile < total_tiles && !failed && !s_fail; tile += gridDim.x, ++t) {
+      for (int tile = blockIdx.x; tile < total_tiles && !failed && !s_fail; tile += gridDim.x) {
         for (int i = 0; i < iters && !failed;) {
-          const int buf = g % kX3PHiBufs;
-          if (!bar_wait(smem_addr(&s_acc_empty[buf]), ((g / kX3PHiBufs) & 1) ^ 1)) {
+          const int buf = g & 1;
+          if (!bar_wait(smem_addr(&s_acc_empty[buf]), ((g >> 1) & 1) ^ 1)) {
             failed = true;
             break;
           }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t acc_hi = tmem_acc + (uint32_t)(buf * 128);
+          const uint32_t acc_hi = tmem_acc + (uint32_t)(buf * 256), acc_lo = acc_hi + 128u;
           const int cend = min(iters, i + chunk_iters);
           const int cbeg = i;
           for (; i < cend; ++i, ++it) {
@@ -188,43 +179,49 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t t0 = tiles + s * kX3PStageBytes, t1 = t0 + kTileBytes, t2 = t0 + 2 * kTileBytes,
                            t3 = t0 + 3 * kTileBytes;
-            // leading terms of this K block
-#pragma unroll
-            for (int j = 0; j < kBK / kUmmaK; ++j) {
-              const uint64_t da = desc_k_major(t0, j);
-              const uint64_t db = MODE == 0 ? desc_mn_major(t2, j) : desc_k_major(t2, j);
-              const uint32_t accumulate = (i > cbeg || j > 0) ? 1u : 0u;
-              asm volatile(
-                  "{\n\t.reg .pred p;\n\t"
-                  "setp.ne.b32 p, %4, 0;\n\t"
-                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                  ::"r"(acc_hi), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-                  : "memory");
-            }
-            if (!p.single) {
-              if (i == 0) {
-                // first cross-term MMA of the tile overwrites the accumulator: the previous tile's must be drained
-                if (!bar_wait(smem_addr(&s_lo_empty), (uint32_t)((t & 1) ^ 1))) {
-                  failed = true;
-                  break;
-                }
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              }
+            if (p.single) {
 #pragma unroll
               for (int j = 0; j < kBK / kUmmaK; ++j) {
-                const uint64_t da = desc_k_major(t0, j), dal = desc_k_major(t1, j);
+                const uint64_t da = desc_k_major(t0, j);
                 const uint64_t db = MODE == 0 ? desc_mn_major(t2, j) : desc_k_major(t2, j);
-                const uint64_t dbl = MODE == 0 ? desc_mn_major(t3, j) : desc_k_major(t3, j);
-                const uint32_t accumulate = (i > 0 || j > 0) ? 1u : 0u;
+                const uint32_t accumulate = (i > cbeg || j > 0) ? 1u : 0u;
                 asm volatile(
-                    "{\n\t.reg .pred p, t;\n\t"
-                    "setp.ne.b32 p, %6, 0;\n\t"
-                    "setp.eq.b32 t, %5, %5;\n\t"
-                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %3, %5, p;\n\t"
-                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %4, %5, t;\n\t}"
-                    ::"r"(acc_lo), "l"(da), "l"(dal), "l"(db), "l"(dbl), "r"(idesc), "r"(accumulate)
+                    "{\n\t.reg .pred p;\n\t"
+                    "setp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                    ::"r"(acc_hi), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
                     : "memory");
               }
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                               smem_addr(&s_empty[s]))
+                           : "memory");
+              continue;
+            }
+#pragma unroll
+            for (int j = 0; j < kBK / kUmmaK; ++j) {
+              uint64_t da, dal, db, dbl;
+              if (MODE == 0) {
+                da = desc_k_major(t0, j);
+                dal = desc_k_major(t1, j);
+                db = desc_mn_major(t2, j);
+                dbl = desc_mn_major(t3, j);
+              } else {
+                da = desc_k_major(t0, j);
+                dal = desc_k_major(t1, j);
+                db = desc_k_major(t2, j);
+                dbl = desc_k_major(t3, j);
+              }
+              const uint32_t accumulate = (i > cbeg || j > 0) ? 1u : 0u;
+              // the two small cross terms are summed apart from the leading term
+              asm volatile(
+                  "{\n\t.reg .pred p, t;\n\t"
+                  "setp.ne.b32 p, %7, 0;\n\t"
+                  "setp.eq.b32 t, %6, %6;\n\t"
+                  "tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %4, %6, p;\n\t"
+                  "tcgen05.mma.cta_group::1.kind::tf32 [%1], %2, %5, %6, t;\n\t"
+                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %4, %6, p;\n\t}"
+                  ::"r"(acc_hi), "r"(acc_lo), "l"(da), "l"(dal), "l"(db), "l"(dbl), "r"(idesc), "r"(accumulate)
+                  : "memory");
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                              smem_addr(&s_empty[s]))
@@ -284,23 +281,22 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
     for (int tile = blockIdx.x; tile < total_tiles && !failed; tile += gridDim.x) {
       float acc[64];
       for (int c = 0; c < n_chunks; ++c, ++g) {
-        const int buf = g % kX3PHiBufs;
-        bool ok = bar_wait(smem_addr(&s_acc_full[buf]), (g / kX3PHiBufs) & 1);
+        const int buf = g & 1;
+        bool ok = bar_wait(smem_addr(&s_acc_full[buf]), (g >> 1) & 1);
         ok = __all_sync(0xffffffffu, ok);
         if (!ok) {
           failed = true;
           break;
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const bool last = c == n_chunks - 1;     // the commit behind the tile's last chunk also covers its cross terms
 #pragma unroll
         for (int gi = 0; gi < 2; ++gi) {
           if (gi < g_per) {
             const int grp = g_first + gi;
             uint32_t r[32], r2[32];
-            tmem_ld32(lane_base + (uint32_t)(buf * 128 + grp * 32), r);
-            if (last && !p.single) {
-              tmem_ld32(lane_base + kX3PLoCol + (uint32_t)(grp * 32), r2);
+            tmem_ld32(lane_base + (uint32_t)(buf * 256 + grp * 32), r);
+            if (!p.single) {
+              tmem_ld32(lane_base + (uint32_t)(buf * 256 + 128 + grp * 32), r2);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) r2[j] = 0u;
@@ -319,11 +315,8 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
         // all TMEM reads of this buffer are done: hand it back
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0)
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&s_acc_empty[buf])) : "memory");
-          if (last && !p.single)
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&s_lo_empty)) : "memory");
-        }
       }
       if (failed) break;
 
