@@ -87,10 +87,10 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
     for (int s = 0; s < kX3PStages; ++s) {
       bar_init(smem_addr(&s_full[s]), 1);
       bar_init(smem_addr(&s_ready[s]), 4);     // one arrival per transform warp
-      bar_init(smem_addr(&s_empty[s]), 1);
+      bar_init(smem_addr(&s_empty[s]), p.single ? 1 : 2);       // both MMA issuers release a stage
     }
     for (int b = 0; b < 2; ++b) {
-      bar_init(smem_addr(&s_acc_full[b]), 1);
+      bar_init(smem_addr(&s_acc_full[b]), p.single ? 1 : 2);    // ... and hand over a chunk
       bar_init(smem_addr(&s_acc_empty[b]), 8);   // one arrival per drain warp
     }
     s_fail = 0;
@@ -152,10 +152,23 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
           }
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ===== MMA issuer: chunks of chunk_iters K blocks alternate between the two TMEM buffers =====
+    } else if ((warp == 1 || (warp == 3 && !p.single)) && lane == 0) {
+      // ===== MMA issuers: chunks of chunk_iters K blocks alternate between the two TMEM buffers =====
+      // TWO issuing threads: warp 1 issues the leading terms (hi x hi -> acc_hi), warp 3 the cross terms
+      // (lo x hi + hi x lo -> acc_lo). One thread issuing all twelve MMAs of a K block needs about as long per
+      // instruction (descriptor arithmetic + the elect / issue sequence on the uniform datapath) as the tensor core
+      // needs to execute it, which capped the pipe at ~50 %; the two accumulators are independent, so the two
+      // streams need no ordering between them. Both wait on the same barriers; a stage (a chunk) is released
+      // (handed to the drain warps) when BOTH have committed: those barriers count two arrivals.
+      // Descriptors: tiles are 1024-byte aligned and every operand offset is a multiple of 16 bytes below 256 KB,
+      // so a descriptor is base + (offset >> 4) on its low word - no per-instruction field packing.
+      const bool lead = warp == 1;
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((MODE == 0 ? 1u : 0u) << 16) |
                              ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+      const uint64_t base_k = desc_k_major(tiles, 0), base_mn = desc_mn_major(tiles, 0);
+      const uint64_t base_b = MODE == 0 ? base_mn : base_k;
+      constexpr uint32_t kStepA = (kUmmaK * 4) >> 4;                       // K-major: 32 bytes per K step
+      constexpr uint32_t kStepB = MODE == 0 ? (1024u >> 4) : kStepA;       // MN-major: 1024 bytes per K step
       int it = 0, g = 0;
       bool failed = false;
       for (int tile = blockIdx.x; tile < total_tiles && !failed && !s_fail; tile += gridDim.x) {
@@ -177,51 +190,36 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
               break;
             }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t t0 = tiles + s * kX3PStageBytes, t1 = t0 + kTileBytes, t2 = t0 + 2 * kTileBytes,
-                           t3 = t0 + 3 * kTileBytes;
-            if (p.single) {
+            const uint32_t soff = (uint32_t)s * (uint32_t)(kX3PStageBytes >> 4);
+            const uint64_t d0 = base_k + soff;                                   // tile 0: A leading part
+            const uint64_t d1 = base_k + soff + (uint32_t)(kTileBytes >> 4);     // tile 1: A residual
+            const uint64_t d2 = base_b + soff + (uint32_t)(2 * kTileBytes >> 4); // tile 2: B leading part
+            const uint64_t d3 = base_b + soff + (uint32_t)(3 * kTileBytes >> 4); // tile 3: B residual
+            if (lead) {
 #pragma unroll
               for (int j = 0; j < kBK / kUmmaK; ++j) {
-                const uint64_t da = desc_k_major(t0, j);
-                const uint64_t db = MODE == 0 ? desc_mn_major(t2, j) : desc_k_major(t2, j);
                 const uint32_t accumulate = (i > cbeg || j > 0) ? 1u : 0u;
                 asm volatile(
                     "{\n\t.reg .pred p;\n\t"
                     "setp.ne.b32 p, %4, 0;\n\t"
                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                    ::"r"(acc_hi), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+                    ::"r"(acc_hi), "l"(d0 + j * kStepA), "l"(d2 + j * kStepB), "r"(idesc), "r"(accumulate)
                     : "memory");
               }
-              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                               smem_addr(&s_empty[s]))
-                           : "memory");
-              continue;
-            }
+            } else {
 #pragma unroll
-            for (int j = 0; j < kBK / kUmmaK; ++j) {
-              uint64_t da, dal, db, dbl;
-              if (MODE == 0) {
-                da = desc_k_major(t0, j);
-                dal = desc_k_major(t1, j);
-                db = desc_mn_major(t2, j);
-                dbl = desc_mn_major(t3, j);
-              } else {
-                da = desc_k_major(t0, j);
-                dal = desc_k_major(t1, j);
-                db = desc_k_major(t2, j);
-                dbl = desc_k_major(t3, j);
+              for (int j = 0; j < kBK / kUmmaK; ++j) {
+                const uint32_t accumulate = (i > cbeg || j > 0) ? 1u : 0u;
+                asm volatile(
+                    "{\n\t.reg .pred p, t;\n\t"
+                    "setp.ne.b32 p, %6, 0;\n\t"
+                    "setp.eq.b32 t, %5, %5;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %3, %5, p;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %4, %5, t;\n\t}"
+                    ::"r"(acc_lo), "l"(d0 + j * kStepA), "l"(d1 + j * kStepA), "l"(d2 + j * kStepB),
+                      "l"(d3 + j * kStepB), "r"(idesc), "r"(accumulate)
+                    : "memory");
               }
-              const uint32_t accumulate = (i > cbeg || j > 0) ? 1u : 0u;
-              // the two small cross terms are summed apart from the leading term
-              asm volatile(
-                  "{\n\t.reg .pred p, t;\n\t"
-                  "setp.ne.b32 p, %7, 0;\n\t"
-                  "setp.eq.b32 t, %6, %6;\n\t"
-                  "tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %4, %6, p;\n\t"
-                  "tcgen05.mma.cta_group::1.kind::tf32 [%1], %2, %5, %6, t;\n\t"
-                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %4, %6, p;\n\t}"
-                  ::"r"(acc_hi), "r"(acc_lo), "l"(da), "l"(dal), "l"(db), "l"(dbl), "r"(idesc), "r"(accumulate)
-                  : "memory");
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                              smem_addr(&s_empty[s]))
