@@ -197,7 +197,7 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             # the same workload description as the ours arm; the CPU arm times a bounded sample of it per step
             # (per-image cost is constant), described under cpu_baseline.sample
-            "config": {"workload": WORKLOAD, "images_per_gpu": IMAGES_PER_GPU},
+            "config": _config("hist", IMAGES_PER_GPU),
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": min(procs, sample), "kind": "port",
                              "sample": f"{total_n // args.steps} images per step, {min(procs, sample)} "
                                        "single-threaded workers (torch-CPU fp32 forward + NumPy statistics; the "
@@ -210,6 +210,13 @@ def run_reference(args):
 # ------------------------------------------------------------------ ours
 def _metric(algo):
     return METRIC if algo == "hist" else METRIC.replace("-A hist --bins 2048", "-A " + algo)
+
+
+def _config(algo, images_per_gpu):
+    """The workload description shared by both arms (the driver compares it)."""
+    return {"workload": _workload(algo), "images_per_gpu": images_per_gpu,
+            "l2": "GPU arm: inputs larger than L2 - every timed kernel streams a 13.6 - 27.2 GB batch of blobs (126 MB "
+                  "L2); CPU arm: not applicable"}
 
 
 def _workload(algo):
@@ -352,16 +359,17 @@ def run_ours(args):
         "metric": _metric(args.algo), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": _workload(args.algo), "images_per_gpu": n_img, "forward_batch": args.batch,
-                   "l2": "inputs larger than L2: every timed kernel streams a %.1f GB batch of blobs "
-                         "(126 MB L2)" % (4 * elems_per_img * args.batch / 1e9),
-                   "forward": ("libdpl_b200 only: 1x1 / 3x3 / strided conv + Gemm on tcgen05 3xTF32 tiles (fp32-accurate), 7x7 stem "
-                               "conv on a direct fp32 kernel, Relu / Add / MaxPool / GlobalAveragePool streaming kernels; range "
-                               "statistics fused into all of their epilogues") if os.environ.get("DPL_ENGINE_TCGEN05", "1") != "0"
-                   else "torch/cuDNN fp32 (TF32 off) stand-in producer",
-                   "statistics": "libdpl_b200.so (K1 segstats on the blobs the forward's kernels did not cover, K2 histogram "
-                                 "variant 7, K3 percentile)",
-                   "resident_blobs": bool(resident_used["v"])},
+        # `config` = the workload, identical in the reference arm's line; how this arm ran it is under `details`
+        "config": _config(args.algo, n_img),
+        "details": {"forward_batch": args.batch,
+                    "blob_bytes_per_forward_batch": 4 * elems_per_img * args.batch,
+                    "forward": ("libdpl_b200 only: 1x1 / 3x3 / strided conv + Gemm on tcgen05 3xTF32 tiles with chunked accumulation "
+                                "(fp32-accurate), 7x7 stem conv on a direct fp32 kernel, Relu / Add / MaxPool / GlobalAveragePool "
+                                "streaming kernels; range statistics fused into all of their epilogues")
+                    if os.environ.get("DPL_ENGINE_TCGEN05", "1") != "0" else "torch/cuDNN fp32 (TF32 off) stand-in producer",
+                    "statistics": "libdpl_b200.so (K1 segstats on the blobs the forward's kernels did not cover, K2 histogram "
+                                  "variant 7, K3 percentile)",
+                    "resident_blobs": bool(resident_used["v"])},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_per_step,
                 "d2h_bytes_per_step": d2h["n"], "ms_per_step": ms_e2e / args.steps},
