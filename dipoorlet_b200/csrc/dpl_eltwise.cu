@@ -283,6 +283,54 @@ extern "C" int dpl_add_f32(const float* d_a, const float* d_b, float* d_y, float
   return 0;
 }
 
+// 3 x 3 / stride 2 / pad 1 (top, left) max pooling with W a multiple of 8 - ResNet's stem pool, the only pooling
+// layer of the measured path. A thread produces FOUR consecutive outputs: per input row two 16-byte loads (columns
+// 8q .. 8q+7) plus the one column to their left, i.e. every input byte is requested once per output row it feeds
+// and the stores are 16 bytes; the one-output-per-thread kernel issued nine scalar loads per output and reached
+// 38 % of the HBM peak. Grid-stride over (plane, output row, column quad).
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_kernel(const float* __restrict__ x, float* __restrict__ y, uint64_t total_quads, int H, int W, int Ho,
+                    int Wo, float* __restrict__ bmin, float* __restrict__ bmax) {
+  __shared__ float s_lo[32], s_hi[32];
+  RangeAcc acc;
+  const int qpr = Wo >> 2;                       // quads per output row
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total_quads; e += stride) {
+    const int q = (int)(e % (uint64_t)qpr);
+    const uint64_t row = e / (uint64_t)qpr;      // plane * Ho + ho
+    const int ho = (int)(row % (uint64_t)Ho);
+    const uint64_t plane = row / (uint64_t)Ho;
+    const float* xp = x + plane * (uint64_t)H * (uint64_t)W;
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+    bool n0 = false, n1 = false, n2 = false, n3 = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int h = 2 * ho - 1 + a;
+      if (h < 0 || h >= H) continue;
+      const float* r = xp + (uint64_t)h * (uint64_t)W + 8 * q;
+      const float4 u = ldg_stream4(reinterpret_cast<const float4*>(r));
+      const float4 v = ldg_stream4(reinterpret_cast<const float4*>(r) + 1);
+      const float l = q > 0 ? __ldg(r - 1) : -INFINITY;     // column 8q - 1 (the left padding for q = 0)
+      // output j covers columns 8q + 2j - 1 .. 8q + 2j + 1
+      m0 = fmaxf(m0, fmaxf(l, fmaxf(u.x, u.y)));
+      m1 = fmaxf(m1, fmaxf(u.y, fmaxf(u.z, u.w)));
+      m2 = fmaxf(m2, fmaxf(u.w, fmaxf(v.x, v.y)));
+      m3 = fmaxf(m3, fmaxf(v.y, fmaxf(v.z, v.w)));
+      n0 |= (l != l) | (u.x != u.x) | (u.y != u.y);
+      n1 |= (u.y != u.y) | (u.z != u.z) | (u.w != u.w);
+      n2 |= (u.w != u.w) | (v.x != v.x) | (v.y != v.y);
+      n3 |= (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+    }
+    const float4 o = make_float4(n0 ? NAN : m0, n1 ? NAN : m1, n2 ? NAN : m2, n3 ? NAN : m3);
+    *reinterpret_cast<float4*>(y + row * (uint64_t)Wo + 4 * q) = o;
+    acc.add(m0);
+    acc.add(m1);
+    acc.add(m2);
+    acc.add(m3);
+  }
+  range_flush(acc, bmin, bmax, s_lo, s_hi);
+}
+
 extern "C" int dpl_maxpool2d_f32(const float* d_x, float* d_y, uint64_t planes, int H, int W, int kh,
                                  int kw, int sh, int sw, int pad_top, int pad_left, int Ho, int Wo,
                                  float* d_blob_min, float* d_blob_max, void* stream) {
@@ -290,6 +338,14 @@ extern "C" int dpl_maxpool2d_f32(const float* d_x, float* d_y, uint64_t planes, 
   DPL_REQUIRE(H > 0 && W > 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && Ho > 0 && Wo > 0, "bad geometry");
   if (planes == 0) return 0;
   DPL_REQUIRE((long long)H * W < (1ll << 31) && (long long)Ho * Wo < (1ll << 31), "plane too large");
+  if (kh == 3 && kw == 3 && sh == 2 && sw == 2 && pad_top == 1 && pad_left == 1 && (W & 7) == 0 && Wo == W / 2 &&
+      Ho == (H + 1) / 2 && (reinterpret_cast<uintptr_t>(d_x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(d_y) & 15u) == 0) {
+    const uint64_t quads = planes * (uint64_t)Ho * (uint64_t)(Wo / 4);
+    maxpool3x3s2_kernel<<<stream_grid(quads), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_y, quads, H, W, Ho, Wo,
+                                                                                          d_blob_min, d_blob_max);
+    DPL_LAUNCH_CHECK("maxpool3x3s2_kernel");
+    return 0;
+  }
   const uint64_t tiles_per_plane = ((uint64_t)Ho * Wo + 255) / 256;
   DPL_REQUIRE(planes * tiles_per_plane < (1ull << 31), "too many tiles");
   auto kern = (kh == 3 && kw == 3) ? maxpool2d_kernel<3, 3> : ((kh == 2 && kw == 2) ? maxpool2d_kernel<2, 2>

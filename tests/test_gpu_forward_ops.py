@@ -39,7 +39,8 @@ def test_add_and_fused_relu_bit_exact(dpl_built, shape):
     assert torch.equal(y, a + b) and torch.equal(r, torch.relu(a + b))
 
 
-@pytest.mark.parametrize("cfg", [((4, 64, 112, 112), 3, 2, 1, False), ((2, 5, 13, 9), 2, 2, 0, False),
+@pytest.mark.parametrize("cfg", [((4, 64, 112, 112), 3, 2, 1, False), ((3, 5, 15, 24), 3, 2, 1, False),
+                                 ((2, 3, 8, 8), 3, 2, 1, False), ((2, 5, 13, 9), 2, 2, 0, False),
                                  ((2, 3, 14, 14), 3, 2, 0, True), ((1, 2, 7, 7), 3, 1, 1, False)])
 def test_maxpool_bit_exact(dpl_built, cfg):
     import torch
@@ -50,6 +51,13 @@ def test_maxpool_bit_exact(dpl_built, cfg):
     want = F.max_pool2d(x, k, s, p, 1, ceil_mode)
     got = K.maxpool2d(x, (k, k), (s, s), p, p, want.shape[2], want.shape[3])
     assert torch.equal(got, want)
+    if k == 3 and s == 2 and p == 1:        # the four-outputs-per-thread kernel: NaN propagates like torch's, range folds
+        x[0, 0, 3, 5] = float("nan")
+        x[-1, -1, 0, 0] = float("nan")
+        want = F.max_pool2d(x, k, s, p, 1, ceil_mode)
+        got = K.maxpool2d(x, (k, k), (s, s), p, p, want.shape[2], want.shape[3])
+        assert torch.equal(torch.isnan(got), torch.isnan(want))
+        assert torch.equal(torch.nan_to_num(got, nan=7.0), torch.nan_to_num(want, nan=7.0))
 
 
 def test_global_avgpool(dpl_built):
