@@ -87,10 +87,10 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
     for (int s = 0; s < kX3PStages; ++s) {
       bar_init(smem_addr(&s_full[s]), 1);
       bar_init(smem_addr(&s_ready[s]), 4);     // one arrival per transform warp
-      bar_init(smem_addr(&s_empty[s]), p.single ? 1 : 2);       // both MMA issuers release a stage
+      bar_init(smem_addr(&s_empty[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
-      bar_init(smem_addr(&s_acc_full[b]), p.single ? 1 : 2);    // ... and hand over a chunk
+      bar_init(smem_addr(&s_acc_full[b]), 1);
       bar_init(smem_addr(&s_acc_empty[b]), 8);   // one arrival per drain warp
     }
     s_fail = 0;
@@ -148,23 +148,25 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
             const int k0 = kb * kBK;
             tma_load_3d(t0, &tmX, k0, m0 + p.c.tap_shift[tap], 0, full);
             tma_load_3d(t2, &tmW, k0, n0, p.c.tap_w[tap], full);
-            if (!p.single && !p.probe_skip_wlo) tma_load_3d(t3, &tmWlo, k0, n0, p.c.tap_w[tap], full);
+            if (!p.single && !p.probe_skip_wlo)
+              tma_load_3d(t2 + (uint32_t)bn * 128u, &tmWlo, k0, n0, p.c.tap_w[tap], full);   // right behind W_hi
           }
         }
       }
-    } else if ((warp == 1 || (warp == 3 && !p.single)) && lane == 0) {
-      // ===== MMA issuers: chunks of chunk_iters K blocks alternate between the two TMEM buffers =====
-      // TWO issuing threads: warp 1 issues the leading terms (hi x hi -> acc_hi), warp 3 the cross terms
-      // (lo x hi + hi x lo -> acc_lo). One thread issuing all twelve MMAs of a K block needs about as long per
-      // instruction (descriptor arithmetic + the elect / issue sequence on the uniform datapath) as the tensor core
-      // needs to execute it, which capped the pipe at ~50 %; the two accumulators are independent, so the two
-      // streams need no ordering between them. Both wait on the same barriers; a stage (a chunk) is released
-      // (handed to the drain warps) when BOTH have committed: those barriers count two arrivals.
+    } else if (warp == 1 && lane == 0) {
+      // ===== MMA issuer: chunks of chunk_iters K blocks alternate between the two TMEM buffers =====
+      // TWO instructions per K step instead of three: the residual tile of the N-side operand sits right behind its
+      // leading tile in shared memory (MODE 0: X | X_lo, MODE 1: W_hi | W_lo), so
+      //     A_hi x [B_hi | B_lo]   is ONE MMA of N = 2 bn into the accumulator pair [acc_hi | acc_lo], and
+      //     A_lo x  B_hi           a second one of N = bn into acc_lo.
+      // Same products, same accumulators, but A_hi is read from shared memory once instead of twice (20 KB instead
+      // of 24 KB per K step through the port that bounds this kernel) and a third fewer instructions to issue.
       // Descriptors: tiles are 1024-byte aligned and every operand offset is a multiple of 16 bytes below 256 KB,
       // so a descriptor is base + (offset >> 4) on its low word - no per-instruction field packing.
-      const bool lead = warp == 1;
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((MODE == 0 ? 1u : 0u) << 16) |
                              ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((MODE == 0 ? 1u : 0u) << 16) |
+                              ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
       const uint64_t base_k = desc_k_major(tiles, 0), base_mn = desc_mn_major(tiles, 0);
       const uint64_t base_b = MODE == 0 ? base_mn : base_k;
       constexpr uint32_t kStepA = (kUmmaK * 4) >> 4;                       // K-major: 32 bytes per K step
@@ -179,7 +181,7 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
             break;
           }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t acc_hi = tmem_acc + (uint32_t)(buf * 256), acc_lo = acc_hi + 128u;
+          const uint32_t acc_hi = tmem_acc + (uint32_t)(buf * 256), acc_lo = acc_hi + (uint32_t)bn;
           const int cend = min(iters, i + chunk_iters);
           const int cbeg = i;
           for (; i < cend; ++i, ++it) {
@@ -193,9 +195,8 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
             const uint32_t soff = (uint32_t)s * (uint32_t)(kX3PStageBytes >> 4);
             const uint64_t d0 = base_k + soff;                                   // tile 0: A leading part
             const uint64_t d1 = base_k + soff + (uint32_t)(kTileBytes >> 4);     // tile 1: A residual
-            const uint64_t d2 = base_b + soff + (uint32_t)(2 * kTileBytes >> 4); // tile 2: B leading part
-            const uint64_t d3 = base_b + soff + (uint32_t)(3 * kTileBytes >> 4); // tile 3: B residual
-            if (lead) {
+            const uint64_t d2 = base_b + soff + (uint32_t)(2 * kTileBytes >> 4); // tile 2 (+ 3): B leading part | residual
+            if (p.single) {
 #pragma unroll
               for (int j = 0; j < kBK / kUmmaK; ++j) {
                 const uint32_t accumulate = (i > cbeg || j > 0) ? 1u : 0u;
@@ -212,12 +213,12 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
                 const uint32_t accumulate = (i > cbeg || j > 0) ? 1u : 0u;
                 asm volatile(
                     "{\n\t.reg .pred p, t;\n\t"
-                    "setp.ne.b32 p, %6, 0;\n\t"
+                    "setp.ne.b32 p, %7, 0;\n\t"
                     "setp.eq.b32 t, %5, %5;\n\t"
-                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %3, %5, p;\n\t"
-                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %4, %5, t;\n\t}"
-                    ::"r"(acc_lo), "l"(d0 + j * kStepA), "l"(d1 + j * kStepA), "l"(d2 + j * kStepB),
-                      "l"(d3 + j * kStepB), "r"(idesc), "r"(accumulate)
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %4, %6, p;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %4, %5, t;\n\t}"
+                    ::"r"(acc_hi), "r"(acc_lo), "l"(d0 + j * kStepA), "l"(d1 + j * kStepA), "l"(d2 + j * kStepB),
+                      "r"(idesc), "r"(idesc2), "r"(accumulate)
                     : "memory");
               }
             }
@@ -294,7 +295,7 @@ x3p_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
             uint32_t r[32], r2[32];
             tmem_ld32(lane_base + (uint32_t)(buf * 256 + grp * 32), r);
             if (!p.single) {
-              tmem_ld32(lane_base + (uint32_t)(buf * 256 + 128 + grp * 32), r2);
+              tmem_ld32(lane_base + (uint32_t)(buf * 256 + bn + grp * 32), r2);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) r2[j] = 0u;
