@@ -234,8 +234,14 @@ int dpl_gemm_tf32(const float* d_a, int a_major, long long lda, long long a_batc
 /* 3xTF32 variant: fp32-accurate products on the TF32 tensor cores,
  *   a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo   (x_hi = top 19 bits, x_lo = x - x_hi),
  * for the calibration forward (activations must stay within fp32 rounding of the reference's
- * fp32 ORT path, dipoorlet/forward_net.py:200-216). d_a_lo = dpl_tf32_residual_f32(d_a) is
- * computed once per weight; the residual of B is formed in shared memory inside the kernel.
+ * fp32 ORT path, dipoorlet/forward_net.py:200-216). The weight operand is split once by
+ * dpl_tf32_split_f32 (pass its d_hi as d_a and its d_lo as d_a_lo; dpl_tf32_residual_f32 of the raw
+ * weight also works but keeps the truncation bias); the residual of B is formed in shared memory
+ * inside the kernel. NCHW 1x1-convolution shapes (a_major 0, b_major 1, shared A, bias per row) run on
+ * the persistent kernel with CHUNKED accumulation (csrc/dpl_x3p.cuh: the tensor core accumulates
+ * DPL_X3_CHUNK = 2 K blocks in TMEM, eight warps drain every chunk into registers with round-to-nearest
+ * adds) - tcgen05's truncating accumulation otherwise shrinks every layer's output by ~1e-6 and the
+ * error compounds over a deep network. DPL_X3_CHUNK=0 selects the round-1 kernels.
  * d_d_relu (optional): a second output max(D, 0) with D's layout — the Relu node behind a Conv is
  * a calibration blob of its own, so the epilogue writes both instead of a second pass.
  * d_blob_min / d_blob_max / d_relu_min / d_relu_max (optional, one float each): fused range statistics of D
