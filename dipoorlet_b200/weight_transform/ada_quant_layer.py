@@ -21,7 +21,7 @@ import torch
 
 from .. import kernels as K
 
-__all__ = ["adaround_reg", "AdaQLayer", "TempDecay", "ZETA", "GAMMA"]
+__all__ = ["adaround_reg", "AdaQLayer", "TempDecay", "ZETA", "GAMMA", "classify_layer"]
 
 ZETA, GAMMA = 1.1, -0.1
 
@@ -57,6 +57,49 @@ class adaround_reg:
     def update(self, it):
         self.beta = self.temp_anneal(it)
         return self.beta
+
+
+def classify_layer(op_type, wshape, attrs, xshape):
+    """Which libdpl_b200 contraction serves this layer (ada_quant_layer.py:224-244 is F.conv2d / F.linear /
+    F.conv_transpose2d on cuDNN / cuBLAS):
+      'gemm'  Gemm on the tcgen05 TF32 tile                         (dpl_gemm_tf32)
+      'c1x1'  1x1 stride-1 convolution straight from NCHW           (dpl_gemm_tf32)
+      'taps'  3x3 (stride 1 / 2) and the other 1x1 convolutions on the tap-table TF32 kernels
+              (dpl_tap_conv_tf32 / dpl_tap_wgrad_tf32) over channel-last staging copies
+      'dw'    depthwise 3x3 / 5x5, exact fp32 on the FMA pipe        (dpl_dwconv2d_*)
+      'stem'  few input channels (3-channel stem): direct fp32 forward, im2col + tcgen05 weight gradient
+      'lib'   anything else (ConvTranspose, grouped, dilated, ... - in neither model family of
+              BASELINE.json): torch / cuDNN, announced once; DPL_STRICT_NATIVE=1 raises instead.
+    TF32 is what the reference's torch conv uses by default (cudnn.allow_tf32 = True).
+    DPL_TCGEN05=0 keeps everything on the library path (debugging only)."""
+    if os.environ.get("DPL_TCGEN05", "1") == "0":
+        return 'lib'
+    if op_type == 'Gemm':
+        ok = len(xshape) == 2 and xshape[1] % 4 == 0 and wshape[0] % 4 == 0
+        return 'gemm' if ok else 'lib'
+    nd = len(wshape) - 2
+    dilation = list(attrs.get("dilations", [1] * nd))
+    if op_type != 'Conv' or len(xshape) != 4 or dilation != [1, 1]:
+        return 'lib'
+    co, cig, kh, kw = wshape
+    ci = xshape[1]
+    stride = list(attrs.get("strides", [1, 1]))
+    pads = list(attrs.get("pads", [0, 0, 0, 0]))
+    groups = int(attrs.get("group", 1))
+    if kh != kw or stride[0] != stride[1] or pads[0] != pads[1] or pads[:2] != pads[2:]:
+        return 'lib'
+    k, st, pd = kh, stride[0], pads[0]
+    if groups == 1:
+        if k == 1 and st == 1 and pd == 0 and ci % 4 == 0 and (xshape[2] * xshape[3]) % 4 == 0:
+            return 'c1x1'
+        if ((k, pd) in ((3, 1), (1, 0))) and st in (1, 2) and ci % 4 == 0 and co % 4 == 0:
+            return 'taps'
+        if ci * k * k <= 256 and (k, st) in ((7, 2), (3, 2), (3, 1), (5, 2), (5, 1)):
+            return 'stem'
+        return 'lib'
+    if groups == ci == co and cig == 1 and k in (3, 5):
+        return 'dw'
+    return 'lib'
 
 
 class AdaQLayer:
@@ -109,44 +152,10 @@ class AdaQLayer:
 
     # ---- forward / backward of the dense op: libdpl_b200 only for both model families ---------------
     def _classify(self, x):
-        """Which libdpl_b200 contraction serves this layer (ada_quant_layer.py:224-244 is F.conv2d / F.linear /
-        F.conv_transpose2d on cuDNN / cuBLAS):
-          'gemm'  Gemm on the tcgen05 TF32 tile                         (dpl_gemm_tf32)
-          'c1x1'  1x1 stride-1 convolution straight from NCHW           (dpl_gemm_tf32)
-          'taps'  3x3 (stride 1 / 2) and the other 1x1 convolutions on the tap-table TF32 kernels
-                  (dpl_tap_conv_tf32 / dpl_tap_wgrad_tf32) over channel-last staging copies
-          'dw'    depthwise 3x3 / 5x5, exact fp32 on the FMA pipe        (dpl_dwconv2d_*)
-          'stem'  few input channels (3-channel stem): direct fp32 forward, im2col + tcgen05 weight gradient
-          'lib'   anything else (ConvTranspose, grouped, dilated, ... - in neither model family of
-                  BASELINE.json): torch / cuDNN, announced once; DPL_STRICT_NATIVE=1 raises instead.
-        TF32 is what the reference's torch conv uses by default (cudnn.allow_tf32 = True).
-        DPL_TCGEN05=0 keeps everything on the library path (debugging only)."""
-        if os.environ.get("DPL_TCGEN05", "1") == "0" or not x.is_contiguous():
+        """Which libdpl_b200 contraction serves this layer for an input of x's shape (see classify_layer)."""
+        if not x.is_contiguous():
             return 'lib'
-        if self.type == 'Gemm':
-            ok = x.dim() == 2 and x.shape[1] % 4 == 0 and self.weight.shape[0] % 4 == 0
-            return 'gemm' if ok else 'lib'
-        if self.type != 'Conv' or x.dim() != 4 or self.dilation != [1, 1]:
-            return 'lib'
-        co, cig, kh, kw = self.weight.shape
-        ci = x.shape[1]
-        if kh != kw or self.stride[0] != self.stride[1] or self.padding[0] != self.padding[1]:
-            return 'lib'
-        pads = list(self.node.attrs.get("pads", [0, 0, 0, 0]))
-        if pads[:2] != pads[2:]:
-            return 'lib'
-        k, st, pd = kh, self.stride[0], self.padding[0]
-        if self.groups == 1:
-            if k == 1 and st == 1 and pd == 0 and ci % 4 == 0 and (x.shape[2] * x.shape[3]) % 4 == 0:
-                return 'c1x1'
-            if ((k, pd) in ((3, 1), (1, 0))) and st in (1, 2) and ci % 4 == 0 and co % 4 == 0:
-                return 'taps'
-            if ci * k * k <= 256 and (k, st) in ((7, 2), (3, 2), (3, 1), (5, 2), (5, 1)):
-                return 'stem'
-            return 'lib'
-        if self.groups == ci == co and cig == 1 and k in (3, 5):
-            return 'dw'
-        return 'lib'
+        return classify_layer(self.type, tuple(self.weight.shape), self.node.attrs, tuple(x.shape))
 
     def _lib_notice(self):
         if os.environ.get("DPL_STRICT_NATIVE", "0") == "1":

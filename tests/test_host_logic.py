@@ -613,3 +613,30 @@ def test_shape_inference_equals_executed_shapes(builder):
     assert len(want) >= 20
     for name, shape in want.items():
         assert list(graph.get_tensor_shape(name)) == shape, name
+
+
+@pytest.mark.parametrize("family", ["r50", "mbv2"])
+def test_every_learnable_layer_has_a_native_contraction(family):
+    """AdaQLayer's kernel choice (classify_layer) for the real ResNet-50 / MobileNetV2 graphs at --ada_bs 64: no
+    learnable layer of either model family may fall to the torch / cuDNN path ('lib')."""
+    from dipoorlet_b200 import workloads as W
+    from dipoorlet_b200.graph import ONNXGraph
+    from dipoorlet_b200.weight_transform.ada_quant_layer import classify_layer
+    from dipoorlet_b200.weight_transform.utils import LEARNABLE_LAYER_TYPES
+    model = W.build_resnet50(seed=0) if family == "r50" else W.build_mobilenetv2(seed=0)
+    graph = ONNXGraph(model, "", "trt")
+    kinds = {}
+    for node in graph.graph.node:
+        if node.op_type not in LEARNABLE_LAYER_TYPES:
+            continue
+        xshape = [64] + list(graph.get_tensor_shape(node.input[0]))[1:]
+        wshape = tuple(graph.get_initializer(node.input[1]).shape)
+        kind = classify_layer(node.op_type, wshape, node.attrs, tuple(xshape))
+        assert kind != 'lib', (node.name, wshape, xshape)
+        kinds[kind] = kinds.get(kind, 0) + 1
+    if family == "r50":
+        # 16 3x3 + 3 strided 1x1 + 5 1x1 on 7x7 maps = 24 tap-table layers
+        assert kinds == {'stem': 1, 'c1x1': 28, 'taps': 24, 'gemm': 1}, kinds
+    else:
+        assert kinds.get('dw') == 17 and kinds.get('stem') == 1 and kinds.get('gemm') == 1, kinds
+        assert sum(kinds.values()) == 53
